@@ -1,0 +1,198 @@
+/*
+ * multike_b200.h -- C-ABI of the B200-native MultiKE training hot path.
+ *
+ * The reference (nju-websoft/MultiKE) has no FFI: its "operators" are TensorFlow-1.x graph
+ * fragments built in code/MultiKE_model.py and code/losses.py and executed by session.run.
+ * Each entry point below names the reference fragment it replaces (file:line under
+ * /root/reference/code).  The Python host side (multike_b200/) binds these with ctypes; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter says "host"; the caller (torch)
+ *     owns all memory and keeps it alive until the stream is synchronised;
+ *   - no hidden allocation, no host synchronisation, re-entrant per stream;
+ *   - return 0 on success, a negative code on failure (-(int)cudaError_t for CUDA failures,
+ *     MKE_EINVAL for bad arguments); never throws; mke_last_error() gives the text;
+ *   - tables are row-major fp32 with a row stride of `stride` floats, stride % 4 == 0,
+ *     base address 16-byte aligned, columns [dim, stride) are zero and stay zero.
+ */
+#ifndef MULTIKE_B200_H_
+#define MULTIKE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKE_ABI_VERSION 1
+#define MKE_EINVAL (-100000)
+#define MKE_MAX_NEG 32        /* K (negatives per positive) supported by the fused kernel */
+#define MKE_MAX_TRY 10        /* base/batch.py:86 max_try=10 */
+
+typedef struct CUstream_st* mke_stream_t; /* == cudaStream_t */
+
+/*
+ * One trainable embedding table as the kernels see it.
+ * Replaces one tf.get_variable + (optional) tf.nn.l2_normalize(var, 1) view
+ * (base/initializers.py:22-26, MultiKE_model.py:92-99) together with the gradient that
+ * optimizer.compute_gradients would build for it (MultiKE_model.py:30).
+ */
+typedef struct mke_table {
+  float*   var;        /* [rows, stride] raw variable V (NOT normalised)                       */
+  float*   grad;       /* [rows, stride] dLoss/dE accumulator, E = l2_normalize(V,1) if
+                          normalised else V; all-zero between steps; NULL => constant table     */
+  uint8_t* touched;    /* [rows] 1 if grad row may be non-zero; all-zero between steps          */
+  int32_t  rows;
+  int32_t  stride;     /* floats per row, multiple of 4                                         */
+  int32_t  dim;        /* logical embedding dimension (<= stride)                               */
+  int32_t  normalised; /* 1: the model reads l2_normalize(var,1) (is_l2_norm=True)              */
+} mke_table_t;
+
+/*
+ * Device-resident set of (h, r, t) triples used to filter negatives
+ * (all_triples_set in base/batch.py:86-107).  Open addressing, linear probing,
+ * key = h<<40 | r<<24 | t, empty slot = UINT64_MAX, capacity a power of two.
+ */
+typedef struct mke_tripleset {
+  uint64_t* slots;
+  uint64_t  capacity;  /* power of two, >= 2 * number of triples                                */
+} mke_tripleset_t;
+
+/*
+ * Candidate pool of one KG for negative sampling (base/batch.py:93-94:
+ * neighbor.get(entity, entities_list)).
+ */
+typedef struct mke_kg_sampler {
+  const int32_t* entity_list;   /* [n_entities] ids of this KG, or NULL => ids are base..base+n-1 */
+  int32_t        entity_base;
+  int32_t        n_entities;
+  const int32_t* neighbours;    /* [rows_of_entity_table, n_neighbours] truncated-eps candidates
+                                   (base/batch.py:119-150) or NULL => uniform over entity_list;
+                                   a row whose first entry is -1 falls back to entity_list      */
+  int32_t        n_neighbours;
+  mke_tripleset_t set;          /* triples of this KG (incl. the swapped "sup" triples, kg.py:59,134) */
+} mke_kg_sampler_t;
+
+int         mke_abi_version(void);
+const char* mke_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t    mke_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Relation view, phase 1.
+ * ------------------------------------------------------------------------------------------ */
+
+/*
+ * Generic TransE-style scored batch = one call of a losses.py function plus its backward:
+ *   negative == 0:  loss += scale * sum_i w_i * log(1 + exp(+||H[ih_i] + M[im_i] - T[it_i]||^2))
+ *   negative == 1:  loss += scale * sum_i w_i * log(1 + exp(-||H[ih_i] + M[im_i] - T[it_i]||^2))
+ * Replaces, by choice of tables/flags:
+ *   relation_logistic_loss           losses.py:4-12   (two calls: positives, negatives)
+ *   attribute_logistic_loss          losses.py:15-27  (tail table = constant literal table)
+ *   relation_logistic_loss_wo_negs   losses.py:30-34
+ *   attribute_logistic_loss_wo_negs  losses.py:37-41
+ *   logistic_loss_wo_negs            losses.py:44-50
+ * and the six tf.nn.embedding_lookup gathers of MultiKE_model.py:123-128 / 164-166 / 194-196.
+ * Gradients are accumulated (+=) into each table's grad (skipped when grad == NULL) and the
+ * rows are flagged in `touched`.  score_out (optional) receives -||.||^2 per triple
+ * (the pos_score / neg_score tensors of losses.py:7-8).
+ */
+int mke_triple_fwd_bwd(const mke_table_t* head, const mke_table_t* mid, const mke_table_t* tail,
+                       const int32_t* ih, const int32_t* im, const int32_t* it, int32_t n,
+                       const float* w_or_null, int32_t negative, float scale,
+                       double* loss_accum, float* score_out_or_null, mke_stream_t stream);
+
+/*
+ * Fused relation-view step, phase 1, with the negative sampler on device:
+ * gather -> score -> logistic loss -> gradient -> scatter-add for one batch made of a kg1
+ * slice and a kg2 slice of positives (base/batch.py:33-42) and K negatives per positive drawn
+ * on the fly with the semantics of generate_neg_triples_fast (base/batch.py:86-116).
+ * Replaces: MultiKE_model.py:123-131 (graph), losses.py:4-12, base/batch.py:33-116 and the
+ * queue/feed_dict plumbing of MultiKE_model.py:295-310.
+ *   pos1/pos2   [len,3] int32 (h,r,t) rows, device
+ *   K           negatives per positive, 0..MKE_MAX_NEG (K == 0 => positives only)
+ *   seed, step  counter-based RNG coordinates; draws are a pure function of
+ *               (seed, step, index of the positive in the batch, try, draw)
+ *   w_or_null   per-positive weights [len1+len2] (applied to the positive term only) or NULL
+ *   pos_scale   multiplier on the positive term (2 for the ckge/ckgp graphs, MultiKE_model.py:168,198)
+ *   neg_out     optional [ (len1+len2) * K, 3 ] int32: the sampled negatives, positive-major
+ *               (what base/batch.py:116 returns) -- for parity tests; NULL in production
+ *   variant     0 = LDG/RED.v4 register path, 1 = TMA bulk-copy / bulk-reduce path
+ */
+int mke_rel_step_sampled(const mke_table_t* ent, const mke_table_t* rel,
+                         const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                         const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                         int32_t K, uint64_t seed, uint64_t step,
+                         const float* w_or_null, float pos_scale,
+                         double* loss_accum, int32_t* neg_out_or_null,
+                         int32_t variant, mke_stream_t stream);
+
+/*
+ * Same fused kernel with the negatives supplied by the caller in structured form
+ * (one corrupted entity + side bit per negative): neg_ent [n,K] int32, neg_side [n] uint32 with
+ * bit j set when negative j replaces the HEAD.  Used by parity tests and by callers that keep
+ * their own sampler.
+ */
+int mke_rel_step_structured(const mke_table_t* ent, const mke_table_t* rel,
+                            const int32_t* pos, int32_t n, int32_t K,
+                            const int32_t* neg_ent, const uint32_t* neg_side,
+                            const float* w_or_null, float pos_scale,
+                            double* loss_accum, int32_t variant, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 2: optimizer.
+ * ------------------------------------------------------------------------------------------ */
+
+/*
+ * For every flagged row: back-propagate the accumulated gradient through l2_normalize
+ * (if table->normalised), apply Adagrad, zero the gradient row, clear the flag.
+ *   u = v * rsqrt(max(|v|^2, 1e-12));  g_v = (g - u (u.g)) * rsqrt(max(|v|^2,1e-12))   [|v|^2 >= 1e-12]
+ *   acc += g_v^2 ;  v -= lr * g_v * rsqrt(acc)
+ * Replaces: the l2_normalize backward + tf.train.AdagradOptimizer.apply_gradients of
+ * MultiKE_model.py:15-31 (dense ApplyAdagrad on every row; rows with zero gradient are a
+ * mathematical no-op and are skipped).  `acc` is this optimizer's accumulator slot
+ * ([rows,stride], initial value 0.1): the reference creates one per generate_optimizer call.
+ */
+int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, float lr, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler pieces (base/batch.py:86-116, attr_batch.py:13-25) usable on their own.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Insert n (h,r,t) rows into an empty (all 0xFF) slot array. */
+int mke_tripleset_build(const mke_tripleset_t* set, const int32_t* triples, int32_t n,
+                        mke_stream_t stream);
+/* out[i] = 1 if triples[i] is in the set else 0. */
+int mke_tripleset_contains(const mke_tripleset_t* set, const int32_t* triples, int32_t n,
+                           uint8_t* out, mke_stream_t stream);
+
+/*
+ * Stand-alone relation negative sampler: writes neg_out [(len1+len2)*K, 3] exactly as the
+ * fused kernel would draw them (same RNG coordinates).
+ */
+int mke_sample_uniform(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                       const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                       int32_t K, uint64_t seed, uint64_t step, int32_t* neg_out,
+                       mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Table utilities.
+ * ------------------------------------------------------------------------------------------ */
+
+/*
+ * out[i, 0:dim] = l2_normalize(var[idx[i]]) (or the raw row if !normalised); idx == NULL => all
+ * rows in order.  out is dense [n, dim].  Replaces tensor.eval(session=) /
+ * tf.nn.embedding_lookup(table, ids).eval() (MultiKE_model.py:263-287, MultiKE_Late.py:16-26).
+ */
+int mke_table_export(const mke_table_t* table, const int32_t* idx_or_null, int32_t n,
+                     float* out, mke_stream_t stream);
+
+/* acc[r, c] = value for c < dim, 0 for pad columns (Adagrad initial_accumulator_value = 0.1). */
+int mke_fill_rows(float* buf, int32_t rows, int32_t stride, int32_t dim, float value,
+                  mke_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIKE_B200_H_ */

@@ -1,0 +1,120 @@
+"""ctypes binding of ``include/multike_b200.h`` (the thin C-ABI over the sm_100a kernels).
+
+There is deliberately NO fallback: if ``csrc/libmultike_b200.so`` is missing or a symbol is
+absent, importing/using the product path raises.  PyTorch is used only to own device memory and
+streams; every pointer handed to the library is ``tensor.data_ptr()``.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+c_i32p = _c.c_void_p  # device pointers travel as integers
+MKE_ABI_VERSION = 1
+MKE_EINVAL = -100000
+MKE_MAX_NEG = 32
+MKE_MAX_TRY = 10
+
+
+class MkeTable(_c.Structure):
+    _fields_ = [
+        ("var", _c.c_void_p),
+        ("grad", _c.c_void_p),
+        ("touched", _c.c_void_p),
+        ("rows", _c.c_int32),
+        ("stride", _c.c_int32),
+        ("dim", _c.c_int32),
+        ("normalised", _c.c_int32),
+    ]
+
+
+class MkeTripleSet(_c.Structure):
+    _fields_ = [("slots", _c.c_void_p), ("capacity", _c.c_uint64)]
+
+
+class MkeKgSampler(_c.Structure):
+    _fields_ = [
+        ("entity_list", _c.c_void_p),
+        ("entity_base", _c.c_int32),
+        ("n_entities", _c.c_int32),
+        ("neighbours", _c.c_void_p),
+        ("n_neighbours", _c.c_int32),
+        ("set", MkeTripleSet),
+    ]
+
+
+_PT = _c.POINTER(MkeTable)
+_PS = _c.POINTER(MkeTripleSet)
+_PK = _c.POINTER(MkeKgSampler)
+_vp, _i32, _u64, _f32 = _c.c_void_p, _c.c_int32, _c.c_uint64, _c.c_float
+
+# name -> (restype, argtypes); one entry per declaration in include/multike_b200.h
+SIGNATURES = {
+    "mke_abi_version": (_i32, []),
+    "mke_last_error": (_c.c_char_p, []),
+    "mke_launch_count": (_u64, []),
+    "mke_triple_fwd_bwd": (_i32, [_PT, _PT, _PT, _vp, _vp, _vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp]),
+    "mke_rel_step_sampled": (_i32, [_PT, _PT, _vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp,
+                                    _f32, _vp, _vp, _i32, _vp]),
+    "mke_rel_step_structured": (_i32, [_PT, _PT, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
+    "mke_rows_apply_adagrad": (_i32, [_PT, _vp, _f32, _vp]),
+    "mke_tripleset_build": (_i32, [_PS, _vp, _i32, _vp]),
+    "mke_tripleset_contains": (_i32, [_PS, _vp, _i32, _vp, _vp]),
+    "mke_sample_uniform": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp]),
+    "mke_table_export": (_i32, [_PT, _vp, _i32, _vp, _vp]),
+    "mke_fill_rows": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen the in-tree library (building it first when nvcc and sources allow)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path) or (_build._nvcc() and not _build.is_fresh()):
+        path = _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError("multike_b200: CUDA library %s is missing (run __graft_entry__.build())" % path)
+    lib = _c.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => the library does not match the header
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mke_abi_version() != MKE_ABI_VERSION:
+        raise RuntimeError("multike_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class MkeError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().mke_last_error().decode("utf-8", "replace")
+        kind = "invalid argument" if rc == MKE_EINVAL else "CUDA error %d" % (-rc)
+        raise MkeError("multike_b200: %s: %s" % (kind, msg))
+
+
+def launch_count():
+    return int(load().mke_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,235 @@
+// Shared device/host helpers for the MultiKE B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/multike_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define MKE_HOST_ONLY 1
+#endif
+
+namespace mke {
+
+constexpr int kWarp = 32;
+constexpr float kNormEps = 1e-12f;  // tf.nn.l2_normalize epsilon [TF semantics]
+constexpr uint64_t kGamma = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kSideDraw = 0xFFFFu;  // draw index reserved for the head/tail coin flip
+
+// ---- error plumbing (host) -----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch();
+int sm_count();
+
+#define MKE_CHECK_ARG(cond, ...)                                                              \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      ::mke::set_error(__VA_ARGS__);                                                          \
+      return MKE_EINVAL;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+#define MKE_CHECK_LAUNCH(what)                                                                \
+  do {                                                                                        \
+    ::mke::count_launch();                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) return ::mke::cuda_fail(e__, what);                               \
+  } while (0)
+
+// ---- counter-based RNG (restated bit-exactly in oracle/sampler.py) --------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ __forceinline__ uint64_t stream_key(uint64_t seed, uint64_t step) {
+  return mix64(seed + kGamma * (step + 1));
+}
+// one 64-bit draw at coordinates (positive index in batch, try, draw index)
+__host__ __device__ __forceinline__ uint64_t draw64(uint64_t skey, uint32_t i, uint32_t tr,
+                                                    uint32_t c) {
+  uint64_t coord = ((uint64_t)i << 20) | ((uint64_t)tr << 16) | (uint64_t)c;
+  return mix64(skey + (coord + 1) * kGamma);
+}
+// unbiased-enough index in [0, n): high 32 bits scaled by n (multiply-high)
+__host__ __device__ __forceinline__ uint32_t draw_index(uint64_t r, uint32_t n) {
+  return (uint32_t)(((r >> 32) * (uint64_t)n) >> 32);
+}
+__host__ __device__ __forceinline__ uint64_t triple_key(int32_t h, int32_t r, int32_t t) {
+  return ((uint64_t)(uint32_t)h << 40) | ((uint64_t)(uint32_t)r << 24) | (uint64_t)(uint32_t)t;
+}
+
+#ifdef __CUDACC__
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+__device__ __forceinline__ void warp_sum3(float& a, float& b, float& c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+__device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_sub(const float4& a, const float4& b) {
+  return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+}
+__device__ __forceinline__ float4 f4_scale(const float4& a, float s) {
+  return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+__device__ __forceinline__ float4 f4_fma(const float4& a, float s, const float4& b) {  // a*s+b
+  return make_float4(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z), fmaf(a.w, s, b.w));
+}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// 16-byte read-only gather of one quarter-sector-aligned piece of a table row
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+// vectorised fire-and-forget reduction: SASS REDG.E.ADD.F32x4 (sm_90+)
+__device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ bool tripleset_contains(const mke_tripleset_t& s, uint64_t key) {
+  if (s.slots == nullptr) return false;
+  const uint64_t mask = s.capacity - 1;
+  uint64_t slot = mix64(key) & mask;
+  while (true) {
+    uint64_t v = __ldg(s.slots + slot);
+    if (v == key) return true;
+    if (v == kEmptySlot) return false;
+    slot = (slot + 1) & mask;
+  }
+}
+
+// candidate pool for replacing `anchor` (base/batch.py:93-94 neighbor.get(e, entities_list))
+struct CandPool {
+  const int32_t* list;  // nullptr => base + idx
+  int32_t base;
+  uint32_t n;
+  __device__ __forceinline__ int32_t at(uint32_t idx) const {
+    return list ? __ldg(list + idx) : base + (int32_t)idx;
+  }
+};
+__device__ __forceinline__ CandPool cand_pool(const mke_kg_sampler_t& kg, int32_t anchor) {
+  CandPool c;
+  if (kg.neighbours != nullptr) {
+    const int32_t* row = kg.neighbours + (size_t)anchor * (size_t)kg.n_neighbours;
+    if (__ldg(row) >= 0) {
+      c.list = row;
+      c.base = 0;
+      c.n = (uint32_t)kg.n_neighbours;
+      return c;
+    }
+  }
+  c.list = kg.entity_list;
+  c.base = kg.entity_base;
+  c.n = (uint32_t)kg.n_entities;
+  return c;
+}
+
+// Sequential statement of generate_neg_triples_fast (base/batch.py:86-116) for ONE positive,
+// run redundantly by all 32 lanes (uniform control flow); s_pick is a 32-int scratch in shared
+// memory private to the warp.  Returns the corrupted entity for lane j (< K) and the side mask
+// (bit j set => negative j replaces the head).
+static __device__ __noinline__ void sample_negs_sequential(const mke_kg_sampler_t& kg, int32_t h,
+                                                    int32_t r, int32_t t, int K, uint64_t skey,
+                                                    uint32_t i, int lane, volatile int32_t* s_pick,
+                                                    int32_t& e_out, uint32_t& side_out) {
+  int n_acc = 0;
+  uint32_t side_mask = 0;
+  int remaining = K;
+  for (uint32_t tr = 0; tr < MKE_MAX_TRY; ++tr) {
+    const bool head_side = (draw64(skey, i, tr, kSideDraw) >> 63) != 0;
+    const CandPool pool = cand_pool(kg, head_side ? h : t);
+    int np = 0;
+    uint32_t c = 0;
+    while (np < remaining) {
+      const int32_t e = pool.at(draw_index(draw64(skey, i, tr, c), pool.n));
+      ++c;
+      bool dup = false;
+      for (int q = 0; q < np; ++q) dup |= (s_pick[n_acc + q] == e);
+      if (dup && c < kSideDraw) continue;  // random.sample draws without replacement
+      __syncwarp();
+      if (lane == 0) s_pick[n_acc + np] = e;
+      __syncwarp();
+      ++np;
+    }
+    int kept = np;
+    if (tr != MKE_MAX_TRY - 1) {  // the last try is accepted unfiltered (batch.py:103-105)
+      kept = 0;
+      for (int q = 0; q < np; ++q) {
+        const int32_t e = s_pick[n_acc + q];
+        const uint64_t key = head_side ? triple_key(e, r, t) : triple_key(h, r, e);
+        if (!tripleset_contains(kg.set, key)) {
+          __syncwarp();
+          if (lane == 0) s_pick[n_acc + kept] = e;
+          __syncwarp();
+          ++kept;
+        }
+      }
+    }
+    if (head_side && kept > 0) {
+      const uint32_t ones = (kept >= 32) ? 0xffffffffu : ((1u << kept) - 1u);
+      side_mask |= ones << n_acc;
+    }
+    n_acc += kept;
+    if (n_acc >= K) break;
+    remaining = K - n_acc;
+  }
+  __syncwarp();
+  e_out = (lane < K) ? s_pick[lane] : -1;
+  side_out = side_mask;
+  __syncwarp();
+}
+
+// Warp-parallel front end: lane j draws negative j of try 0; falls back to the sequential
+// statement when a duplicate or a filtered candidate shows up (about 0.3 % of positives).
+__device__ __forceinline__ void sample_negs_warp(const mke_kg_sampler_t& kg, int32_t h, int32_t r,
+                                                 int32_t t, int K, uint64_t skey, uint32_t i,
+                                                 int lane, volatile int32_t* s_pick,
+                                                 int32_t& e_out, uint32_t& side_out) {
+  const bool head_side = (draw64(skey, i, 0, kSideDraw) >> 63) != 0;
+  const CandPool pool = cand_pool(kg, head_side ? h : t);
+  int32_t e = -1 - lane;  // distinct dummies for idle lanes
+  bool bad = false;
+  if (lane < K) {
+    e = pool.at(draw_index(draw64(skey, i, 0, (uint32_t)lane), pool.n));
+    const uint64_t key = head_side ? triple_key(e, r, t) : triple_key(h, r, e);
+    bad = tripleset_contains(kg.set, key);
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, e);
+  bad |= (peers & (peers - 1)) != 0;  // another lane drew the same entity
+  if (__any_sync(0xffffffffu, bad)) {
+    sample_negs_sequential(kg, h, r, t, K, skey, i, lane, s_pick, e_out, side_out);
+    return;
+  }
+  e_out = (lane < K) ? e : -1;
+  side_out = head_side ? ((K >= 32) ? 0xffffffffu : ((1u << K) - 1u)) : 0u;
+}
+#endif  // __CUDACC__
+
+}  // namespace mke

@@ -1,0 +1,97 @@
+"""Bit-exact CPU restatement of the ON-DEVICE negative sampler (multike_b200/csrc/mke_common.cuh:
+mix64 / stream_key / draw64 / draw_index / sample_negs_sequential).
+
+The device sampler keeps the semantics of generate_neg_triples_fast (base/batch.py:86-116) --
+one head/tail coin per round, draws without replacement inside a round, known triples filtered,
+last round unfiltered, exactly K per positive, positive-major output -- but replaces CPython's
+Mersenne Twister by a counter-based generator so that CPU and GPU agree bit for bit.  Order
+inside a positive is draw order (the reference's is Python-set order, i.e. unspecified).
+"""
+import numpy as np
+
+MASK = (1 << 64) - 1
+GAMMA = 0x9E3779B97F4A7C15
+SIDE_DRAW = 0xFFFF
+MAX_TRY = 10
+
+
+def mix64(x):
+    x &= MASK
+    x ^= x >> 30
+    x = (x * 0xBF58476D1CE4E5B9) & MASK
+    x ^= x >> 27
+    x = (x * 0x94D049BB133111EB) & MASK
+    x ^= x >> 31
+    return x
+
+
+def stream_key(seed, step):
+    return mix64((seed + GAMMA * (step + 1)) & MASK)
+
+
+def draw64(skey, i, tr, c):
+    coord = (i << 20) | (tr << 16) | c
+    return mix64((skey + (coord + 1) * GAMMA) & MASK)
+
+
+def draw_index(r, n):
+    return ((r >> 32) * n) >> 32
+
+
+class KG:
+    """Candidate pool + filter set of one KG (mirror of mke_kg_sampler_t)."""
+
+    def __init__(self, entity_base=0, n_entities=0, entity_list=None, triples=None, neighbours=None):
+        self.entity_list = None if entity_list is None else [int(e) for e in entity_list]
+        self.entity_base = int(entity_base)
+        self.n_entities = len(self.entity_list) if self.entity_list is not None else int(n_entities)
+        self.set = None if triples is None else {tuple(int(x) for x in t) for t in np.asarray(triples).reshape(-1, 3)}
+        self.neighbours = None if neighbours is None else np.asarray(neighbours)
+
+    def pool(self, anchor):
+        if self.neighbours is not None and self.neighbours[anchor, 0] >= 0:
+            row = self.neighbours[anchor]
+            return (lambda k: int(row[k])), len(row)
+        if self.entity_list is not None:
+            return (lambda k: self.entity_list[k]), self.n_entities
+        return (lambda k: self.entity_base + k), self.n_entities
+
+    def contains(self, h, r, t):
+        return self.set is not None and (h, r, t) in self.set
+
+
+def sample_one(kg, h, r, t, K, skey, i):
+    """Negatives of positive number i of the batch: list of K (h', r, t') tuples."""
+    picks, sides = [], []
+    remaining = K
+    for tr in range(MAX_TRY):
+        head_side = (draw64(skey, i, tr, SIDE_DRAW) >> 63) != 0
+        at, n = kg.pool(h if head_side else t)
+        cur, c = [], 0
+        while len(cur) < remaining:
+            e = at(draw_index(draw64(skey, i, tr, c), n))
+            c += 1
+            if e in cur and c < SIDE_DRAW:
+                continue
+            cur.append(e)
+        if tr != MAX_TRY - 1:
+            cur = [e for e in cur if not (kg.contains(e, r, t) if head_side else kg.contains(h, r, e))]
+        picks += cur
+        sides += [head_side] * len(cur)
+        if len(picks) >= K:
+            break
+        remaining = K - len(picks)
+    return [((e, r, t) if hs else (h, r, e)) for e, hs in zip(picks, sides)]
+
+
+def sample_batch(pos1, kg1, pos2, kg2, K, seed, step):
+    """mke_sample_uniform / the sampler fused into mke_rel_step_sampled: int32 [(n1+n2)*K, 3]."""
+    skey = stream_key(seed, step)
+    pos1 = np.asarray(pos1, dtype=np.int64).reshape(-1, 3)
+    pos2 = np.asarray(pos2, dtype=np.int64).reshape(-1, 3)
+    out = []
+    for i, (h, r, t) in enumerate(pos1):
+        out += sample_one(kg1, int(h), int(r), int(t), K, skey, i)
+    for k, (h, r, t) in enumerate(pos2):
+        out += sample_one(kg2, int(h), int(r), int(t), K, skey, len(pos1) + k)
+    return np.asarray(out, dtype=np.int32).reshape(-1, 3)
