@@ -1,0 +1,49 @@
+"""The C-ABI library must load on a CPU-only box and export every symbol include/*.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from multike_b200 import _cabi
+from multike_b200 import build as mke_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "multike_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mke_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_cabi.SIGNATURES)
+
+
+def test_library_builds_loads_and_exports_everything():
+    path = mke_build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    lib2 = _cabi.load()
+    assert lib2.mke_abi_version() == _cabi.MKE_ABI_VERSION
+    assert lib2.mke_launch_count() == 0 or lib2.mke_launch_count() > 0
+
+
+def test_bad_arguments_are_reported_not_thrown():
+    lib = _cabi.load()
+    rc = lib.mke_rows_apply_adagrad(None, None, 0.1, None)
+    assert rc == _cabi.MKE_EINVAL
+    assert b"apply needs" in lib.mke_last_error()
+    with pytest.raises(_cabi.MkeError):
+        _cabi.check(rc)
+
+
+def test_struct_layout_matches_header():
+    # mke_table_t: 3 pointers + 4 int32; mke_tripleset_t: pointer + u64; mke_kg_sampler_t
+    assert ctypes.sizeof(_cabi.MkeTable) == 3 * 8 + 4 * 4
+    assert ctypes.sizeof(_cabi.MkeTripleSet) == 16
+    assert ctypes.sizeof(_cabi.MkeKgSampler) == 8 + 4 + 4 + 8 + 4 + 4 + 16
