@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- positive triples/s through the relation-view TRAIN STEP (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: fused gather -> score -> logistic loss ->
+gradient scatter-add with on-device negative sampling (phase 1) + per-touched-row
+normalise-backward + Adagrad (phase 2) on the entity and relation tables.  Workload at N=1 is
+BASELINE.json configs[1]: DBP-WD-100K-shaped (200 000 entities, 550 relations, 912 068 triples,
+synthetic with the measured degree laws), dim=75, batch=20 000, neg=10.
+
+  value      whole-job positives/s with the triple lists resident in HBM (CUDA events)
+  e2e        same metric through the public step API with HOST (pinned) positives copied H2D and
+             the batch loss read D2H every step
+  roofline   phase-1 kernel: algorithmic bytes per launch / mean launch duration (CUDA events
+             around every phase-1 launch of the timed region) vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  oracle port of the reference CPU path on a bounded sample (rank 0, N=1)
+`--impl reference` times that CPU path alone and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pos_triples_per_sec_rel_view_train_step"
+UNIT = "triples/s"
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "dwy100k_rel_d75_b20000_k10": dict(shape="DWY100K", dim=75, batch=20000, neg=10),
+    # BASELINE.json configs[4]
+    "synth1m_rel_d128_b20000_k25": dict(shape="SYNTH_1M", dim=128, batch=20000, neg=25),
+}
+DEFAULT_WORKLOAD = "dwy100k_rel_d75_b20000_k10"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def bytes_per_positive(dim, K):
+    """rows read 3+K, gradient rows written 3+K, 12 B of indices; rows at dim*4 B."""
+    return 2 * (3 + K) * dim * 4 + 12
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, rank=0, world=1):
+    from multike_b200 import synthetic
+    w = WORKLOADS[name]
+    shape = getattr(synthetic, w["shape"])
+    # weak scaling: every rank trains its own DWY100K-shaped pair of KGs (seeded by rank)
+    kgs = synthetic.make_kgs(shape, seed=1234 + rank)
+    return w, kgs
+
+
+def cpu_baseline_run(name, steps, warmup):
+    from oracle import cpu_path
+    w, kgs = make_workload(name)
+    r = cpu_path.run_steps(kgs["triples1"], kgs["triples2"], kgs["n_ent"], kgs["n_rel"], kgs["ent_split"], w["dim"],
+                           w["batch"], w["neg"], steps=steps, warmup=warmup, workers=4)
+    r["value"] = r["positives"] / r["seconds"]
+    return r
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; TF-1.x is not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    w = WORKLOADS[name]
+    steps = max(1, min(args.steps, 12))   # bounded sample: one step is ~0.5-1 s of all host cores
+    warmup = max(1, min(args.warmup, 2))
+    r = cpu_baseline_run(name, steps, warmup)
+    sample = "%d steps of batch %d (K=%d) of the same workload; sampler in %d forked processes + dense torch-CPU step" % (
+        steps, w["batch"], w["neg"], r["sampler_workers"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "dim": w["dim"], "batch": w["batch"], "neg": w["neg"],
+                   "note": "oracle port of the TF-1.x CPU graph (dense semantics) + reference sampler restatement"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=460)
+    ap.add_argument("--warmup", type=int, default=46)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("MKE_VARIANT", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from multike_b200 import _cabi
+    from multike_b200.relation_view import RelationView
+    _cabi.load()
+
+    w, kgs = make_workload(args.workload, rank, world)
+    K, dim, B = w["neg"], w["dim"], w["batch"]
+    gen = torch.Generator().manual_seed(20190754 + rank)
+    rv = RelationView(kgs["n_ent"], kgs["n_rel"], dim, kgs["triples1"], kgs["triples2"], kgs["ent_split"],
+                      batch_size=B, neg_num=K, lr=0.001, seed=1234 + rank, variant=args.variant, generator=gen)
+    spe = rv.triple_steps
+    warmup = max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ---------------------------------------------------------------
+    step_no = 0
+    for _ in range(warmup):
+        rv.step_resident(step_no % spe)
+        step_no += 1
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    rv.phase1_events = []
+    launches0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    positives = 0
+    e0.record()
+    for _ in range(args.steps):
+        positives += rv.step_resident(step_no % spe)
+        step_no += 1
+    e1.record()
+    barrier()
+    launches = _cabi.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    p1_ms = sum(a.elapsed_time(b) for a, b in rv.phase1_events) / max(len(rv.phase1_events), 1)
+    rv.phase1_events = None
+
+    # ---- end-to-end leg: host positives in, loss out, every step -----------------------------
+    import numpy as np
+    t1_host = torch.from_numpy(np.ascontiguousarray(kgs["triples1"])).pin_memory()
+    t2_host = torch.from_numpy(np.ascontiguousarray(kgs["triples2"])).pin_memory()
+    staging = rv.make_staging()
+    e2e_pos, h2d = 0, 0
+
+    def host_step(s):
+        (a1, b1), (a2, b2) = rv.step_slices(s % spe)
+        return rv.step_host(t1_host[a1:b1], t2_host[a2:b2], staging)
+
+    for s in range(3):
+        host_step(s)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for s in range(args.steps):
+        _, n = host_step(step_no + s)
+        e2e_pos += n
+        h2d += n * 12
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+
+    # ---- reduce over ranks: max time, sum positives -----------------------------------------
+    stats = torch.tensor([ms, e2e_ms, p1_ms], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([positives, e2e_pos, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms, e2e_ms, p1_ms = [float(x) for x in stats.cpu()]
+    positives, e2e_pos, launches = [float(x) for x in counts.cpu()]
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        pos_per_launch = positives / world / args.steps  # per rank per phase-1 launch
+        alg_bytes = pos_per_launch * bytes_per_positive(dim, K)
+        achieved = alg_bytes / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": positives / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "entities": kgs["n_ent"], "relations": kgs["n_rel"],
+                       "triples": int(rv.n1 + rv.n2), "dim": dim, "batch": B, "neg": K, "steps_per_epoch": spe,
+                       "variant": ["ldg_red", "tma_bulk"][args.variant],
+                       "l2": "no flush: step working set (var+grad+Adagrad slot of the entity table, %d MB) exceeds "
+                             "the 126 MB L2 and each step touches a different random row set"
+                             % (3 * kgs["n_ent"] * rv.ent.stride * 4 // 2 ** 20),
+                       "parallelism": "1 process per GPU; independent KG pair per rank" if world > 1 else "single GPU"},
+            "clocks": clk,
+            "e2e": {"value": e2e_pos / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / world / args.steps,
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "rel_fused (phase 1)",
+                         "peak_source": peak_kind, "launch_ms": p1_ms,
+                         "bytes_per_positive": bytes_per_positive(dim, K)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_baseline_run(args.workload, args.cpu_steps, 1)
+            line["cpu_baseline"] = {
+                "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                "sample": "%d steps of batch %d (K=%d): reference sampler restatement in %d forked processes + "
+                          "dense-semantics torch-CPU step (oracle port of the TF-1.x graph)" % (
+                              args.cpu_steps, B, K, r["sampler_workers"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
