@@ -51,8 +51,9 @@ typedef struct mke_table {
 
 /*
  * Device-resident set of (h, r, t) triples used to filter negatives
- * (all_triples_set in base/batch.py:86-107).  Open addressing, linear probing,
- * key = h<<40 | r<<24 | t, empty slot = UINT64_MAX, capacity a power of two.
+ * (all_triples_set in base/batch.py:86-107).  Open addressing over buckets of four 64-bit keys
+ * (one 32-byte sector, filled front to back), linear probing over buckets;
+ * key = h<<40 | r<<24 | t, empty slot = UINT64_MAX, capacity (in keys) a power of two >= 8.
  */
 typedef struct mke_tripleset {
   uint64_t* slots;
@@ -118,7 +119,9 @@ int mke_triple_fwd_bwd(const mke_table_t* head, const mke_table_t* mid, const mk
  *   pos_scale   multiplier on the positive term (2 for the ckge/ckgp graphs, MultiKE_model.py:168,198)
  *   neg_out     optional [ (len1+len2) * K, 3 ] int32: the sampled negatives, positive-major
  *               (what base/batch.py:116 returns) -- for parity tests; NULL in production
- *   variant     0 = LDG/RED.v4 register path, 1 = TMA bulk-copy / bulk-reduce path
+ *   variant     0 = quarter-warp register path (default; falls back to 2 for strides without an
+ *               instantiation), 1 = TMA bulk-copy / bulk-reduce path, 2 = warp-per-positive
+ *               LDG / RED.v4 path (any stride <= 256)
  */
 int mke_rel_step_sampled(const mke_table_t* ent, const mke_table_t* rel,
                          const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,

@@ -3,6 +3,7 @@
 // MultiKE_model.py:15-31 (base/initializers.py:26 for the normalised view).  Rows whose gradient
 // is identically zero are a no-op under Adagrad (acc += 0, v -= 0) and are skipped via the
 // `touched` byte map written by phase 1.
+#include <cstdlib>
 #include "mke_common.cuh"
 
 namespace mke {
@@ -79,6 +80,134 @@ __global__ void __launch_bounds__(kApplyThreads)
   }
 }
 
+// ---- quarter-warp layout (default for strides 32/64/80/104/128) -------------------------------
+// A warp scans 32 flag bytes, then its four quarters take four flagged rows at a time; lane
+// `sub` of a quarter owns FPL = stride/8 floats of the row (same layout as mke_rel_q8.cu), so the
+// three reads and three writes of a row are full 128-byte segments and two 3-step shuffle
+// reductions replace the 5-step warp ones.  All 9 loads of a row are issued before first use.
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+template <int FPL>
+__device__ __forceinline__ void q_load(const float* __restrict__ row, int sub, float (&x)[FPL]) {
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(row + (c * 8 + sub) * 4);
+    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+  }
+  const float* tail = row + NV4 * 32 + REM * sub;
+  if constexpr (REM == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(tail);
+    x[4 * NV4] = v.x; x[4 * NV4 + 1] = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < REM; ++k) x[4 * NV4 + k] = tail[k];
+  }
+}
+template <int FPL>
+__device__ __forceinline__ void q_store(float* __restrict__ row, int sub, const float (&x)[FPL]) {
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c)
+    *reinterpret_cast<float4*>(row + (c * 8 + sub) * 4) =
+        make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+  float* tail = row + NV4 * 32 + REM * sub;
+  if constexpr (REM == 2) {
+    *reinterpret_cast<float2*>(tail) = make_float2(x[4 * NV4], x[4 * NV4 + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < REM; ++k) tail[k] = x[4 * NV4 + k];
+  }
+}
+
+template <int FPL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    apply_adagrad_q8_kernel(float* __restrict__ var, float* __restrict__ grad,
+                            uint8_t* __restrict__ touched, float* __restrict__ acc, int rows,
+                            int normalised, float lr) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr int stride = FPL * 8;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  const int q = lane >> 3;
+  const int gwarp = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * WARPS;
+  for (int base = gwarp * 32; base < rows; base += nwarps * 32) {
+    const int my = base + lane;
+    const bool flag = (my < rows) && (touched[my] != 0);
+    uint32_t m = __ballot_sync(kFullMask, flag);
+    if (flag) touched[my] = 0;
+    while (m) {  // warp-uniform
+      // quarter q takes the q-th lowest flagged row of the remaining ones
+      uint32_t mm = m;
+      int bit = -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int b = mm ? (__ffs(mm) - 1) : -1;
+        if (k == q) bit = b;
+        mm &= mm - 1;
+      }
+      m = mm;
+      const bool on = bit >= 0;
+      const size_t off = (size_t)(base + (on ? bit : 0)) * stride;
+      float g[FPL], v[FPL], a[FPL];
+      q_load<FPL>(grad + off, sub, g);
+      q_load<FPL>(var + off, sub, v);
+      q_load<FPL>(acc + off, sub, a);
+      float inv = 1.f, coef = 0.f;
+      if (normalised) {
+        float ss = 0.f, vg = 0.f;
+#pragma unroll
+        for (int k = 0; k < FPL; ++k) {
+          ss = fmaf(v[k], v[k], ss);
+          vg = fmaf(v[k], g[k], vg);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          ss += __shfl_xor_sync(kFullMask, ss, o);
+          vg += __shfl_xor_sync(kFullMask, vg, o);
+        }
+        // y = v * rsqrt(max(|v|^2, eps)); the max() routes no gradient to |v|^2 below eps
+        inv = rsqrtf(fmaxf(ss, kNormEps));
+        coef = (ss >= kNormEps) ? vg * inv * inv : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < FPL; ++k) {
+        const float gv = (g[k] - v[k] * coef) * inv;
+        a[k] = fmaf(gv, gv, a[k]);
+        // var -= grad * lr * rsqrt(accum)   (ApplyAdagrad, no epsilon) [TF semantics]
+        v[k] -= gv * lr * (a[k] > 0.f ? rsqrtf(a[k]) : 0.f);
+        g[k] = 0.f;
+      }
+      if (on) {
+        q_store<FPL>(var + off, sub, v);
+        q_store<FPL>(acc + off, sub, a);
+        q_store<FPL>(grad + off, sub, g);
+      }
+    }
+  }
+}
+
+template <int FPL, int THREADS, int MINB>
+static int launch_apply_q8(const mke_table_t* t, float* acc, float lr, cudaStream_t stream) {
+  auto kern = apply_adagrad_q8_kernel<FPL, THREADS, MINB>;
+  constexpr int WARPS = THREADS / 32;
+  static int per_sm_cached = 0;
+  if (per_sm_cached == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    per_sm_cached = per_sm;
+  }
+  const int full = sm_count() * per_sm_cached;
+  int need = ((t->rows + 31) / 32 + WARPS - 1) / WARPS;
+  if (need > full) need = full;
+  if (need < 1) need = 1;
+  kern<<<need, THREADS, 0, stream>>>(t->var, t->grad, t->touched, acc, t->rows, t->normalised, lr);
+  MKE_CHECK_LAUNCH("apply_adagrad_q8_kernel");
+  return 0;
+}
+
 template <int NV>
 static int launch_apply(const mke_table_t* t, float* acc, float lr, cudaStream_t stream) {
   auto kern = apply_adagrad_kernel<NV>;
@@ -110,6 +239,17 @@ extern "C" int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, floa
   const int nv = ((table->dim + 3) / 4 + 31) / 32;
   MKE_CHECK_ARG(nv <= 8, "dim too large");
   cudaStream_t s = (cudaStream_t)stream;
+  static const int generic = getenv("MKE_APPLY_GENERIC") ? atoi(getenv("MKE_APPLY_GENERIC")) : 0;
+  if (!generic) {
+    switch (table->stride) {
+      case 32: return launch_apply_q8<4, 128, 12>(table, acc, lr, s);
+      case 64: return launch_apply_q8<8, 128, 10>(table, acc, lr, s);
+      case 80: return launch_apply_q8<10, 128, 8>(table, acc, lr, s);
+      case 104: return launch_apply_q8<13, 128, 8>(table, acc, lr, s);
+      case 128: return launch_apply_q8<16, 128, 6>(table, acc, lr, s);
+      default: break;
+    }
+  }
   switch (nv) {
     case 1: return launch_apply<1>(table, acc, lr, s);
     case 2: return launch_apply<2>(table, acc, lr, s);

@@ -113,15 +113,20 @@ __device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
                : "memory");
 }
 
+// Triple set: open addressing over BUCKETS of four 64-bit keys (one 32-byte sector); a bucket
+// fills front to back and never empties, so a lookup reads one sector and stops at the first
+// bucket whose last slot is still empty.  A miss costs one memory round trip at load <= 0.5.
+constexpr int kBucketSlots = 4;
 __device__ __forceinline__ bool tripleset_contains(const mke_tripleset_t& s, uint64_t key) {
   if (s.slots == nullptr) return false;
-  const uint64_t mask = s.capacity - 1;
-  uint64_t slot = mix64(key) & mask;
+  const uint64_t mask = (s.capacity / kBucketSlots) - 1;
+  uint64_t b = mix64(key) & mask;
   while (true) {
-    uint64_t v = __ldg(s.slots + slot);
-    if (v == key) return true;
-    if (v == kEmptySlot) return false;
-    slot = (slot + 1) & mask;
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(s.slots + b * kBucketSlots);
+    const ulonglong2 lo = __ldg(p), hi = __ldg(p + 1);
+    if (lo.x == key || lo.y == key || hi.x == key || hi.y == key) return true;
+    if (hi.y == kEmptySlot) return false;
+    b = (b + 1) & mask;
   }
 }
 

@@ -9,48 +9,13 @@
 //              SASS UBLKCP) and gradient rows returned with cp.reduce.async.bulk .add.f32
 //              (SASS UBLKRED) -- one bulk op per 300-byte row instead of 19 lanes of LSU work.
 // The arithmetic is identical in both; DESIGN.md has the measurements behind the default.
-#include "mke_common.cuh"
+#include <cstdlib>
+#include "mke_rel.cuh"
 
 namespace mke {
 
-struct RelStepParams {
-  const float* ent_var;
-  float* ent_grad;
-  uint8_t* ent_touched;
-  const float* rel_var;
-  float* rel_grad;
-  uint8_t* rel_touched;
-  int stride;    // floats per row (both tables)
-  int nchunk;    // float4 pieces per row that carry data = ceil(dim/4)
-  int ent_norm;  // read l2_normalize(ent_var,1)
-  int rel_norm;
-  const int32_t* pos1;
-  int len1;
-  const int32_t* pos2;
-  int len2;
-  mke_kg_sampler_t kg1, kg2;
-  int K;
-  int sampled;  // 1: draw negatives on device, 0: read neg_ent / neg_side
-  uint64_t skey;
-  const int32_t* neg_ent;
-  const uint32_t* neg_side;
-  const float* w;
-  float pos_scale;
-  double* loss;
-  int32_t* neg_out;
-};
-
 constexpr int kRelThreads = 256;
 constexpr int kRelWarps = kRelThreads / 32;
-
-// log(1+exp(x)) and sigmoid(x) exactly as the reference writes them (losses.py:9-10: naive
-// tf.log(1 + tf.exp(x)); no softplus stabilisation -- x = ||.||^2 <= 9 for unit rows)
-__device__ __forceinline__ void softplus_sigmoid(float x, float& sp, float& sg) {
-  const float ex = expf(x);
-  const float one_p = 1.0f + ex;
-  sp = logf(one_p);
-  sg = ex / one_p;
-}
 
 __device__ __forceinline__ void block_loss_commit(float loss_local, double* loss) {
   __shared__ float s_loss[kRelWarps];
@@ -512,9 +477,15 @@ static int grid_for(Kern kern, int threads, size_t smem, int warps_per_block, in
 }
 
 static int launch_rel(RelStepParams& p, int variant, cudaStream_t stream) {
+  static const int dbg = getenv("MKE_DEBUG_SKIP") ? atoi(getenv("MKE_DEBUG_SKIP")) : 0;
+  p.dbg = dbg;
   const int n = p.len1 + p.len2;
   if (n <= 0) return 0;
   const int nv = (p.nchunk + 31) / 32;
+  if (variant == 0) {
+    const int rc = launch_rel_q8(p, stream);
+    if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = no instantiation for this stride
+  }
   if (variant == 1) {
     const size_t smem = (size_t)kTmaWarps * 4 * (3 + p.K) * p.stride * sizeof(float);
     if (smem <= 200 * 1024) {

@@ -1,0 +1,49 @@
+// Parameters and small device helpers shared by the fused relation-view kernels.
+#pragma once
+#include "mke_common.cuh"
+
+namespace mke {
+
+struct RelStepParams {
+  const float* ent_var;
+  float* ent_grad;
+  uint8_t* ent_touched;
+  const float* rel_var;
+  float* rel_grad;
+  uint8_t* rel_touched;
+  int stride;    // floats per row (both tables)
+  int nchunk;    // float4 pieces per row that carry data = ceil(dim/4)
+  int ent_norm;  // read l2_normalize(ent_var,1)
+  int rel_norm;
+  const int32_t* pos1;
+  int len1;
+  const int32_t* pos2;
+  int len2;
+  mke_kg_sampler_t kg1, kg2;
+  int K;
+  int sampled;  // 1: draw negatives on device, 0: read neg_ent / neg_side
+  uint64_t skey;
+  const int32_t* neg_ent;
+  const uint32_t* neg_side;
+  const float* w;
+  float pos_scale;
+  double* loss;
+  int32_t* neg_out;
+  int dbg;  // timing experiments only (MKE_DEBUG_SKIP): bit0 no rel RED, bit1 no touched, bit2 no loss atomic, bit3 no ent RED, bit4 no hash probe
+};
+
+// log(1+exp(x)) and sigmoid(x) as the reference writes them (losses.py:9-10: naive
+// tf.log(1 + tf.exp(x)); no softplus stabilisation -- x = +-||.||^2, |x| <= 9 for unit rows).
+// MUFU.EX2 / MUFU.LG2 / MUFU.RCP forms: relative error of exp <= 2^-21 on |x| <= 16, absolute
+// error of log <= 2^-21 -- far inside the 1e-5 loss / 1e-4 gradient tolerances.
+__device__ __forceinline__ void softplus_sigmoid(float x, float& sp, float& sg) {
+  const float ex = __expf(x);
+  const float one_p = 1.0f + ex;
+  sp = __logf(one_p);
+  sg = __fdividef(ex, one_p);
+}
+
+// quarter-warp kernel (mke_rel_q8.cu); returns 1 when the stride has no instantiation
+int launch_rel_q8(const RelStepParams& p, cudaStream_t stream);
+
+}  // namespace mke

@@ -1,0 +1,543 @@
+// Relation view, phase 1, quarter-warp layout (the default data path).
+//
+// One positive triple with its K single-side-corrupted negatives is owned by a QUARTER warp
+// (8 lanes); a row of `stride` floats is spread over the 8 lanes as FPL = stride/8 floats per
+// lane (stride 80: two float4 + one float2 per lane, i.e. one 128-byte segment per 16-byte
+// load instruction and quarter).  Against the warp-per-positive kernel (mke_rel.cu) this
+//   * keeps all 32 lanes busy (a 75-float row only fills 19 lanes of float4),
+//   * amortises the per-row overhead (two reductions, exp/log, addressing) over 4 rows,
+//   * shortens reductions to 3 shuffle steps,
+//   * holds only two live row vectors per positive (base, acc) so that >= 128 positives are in
+//     flight per SM -- the kernel is a single wave at batch 20 000 and is bounded by L2/HBM
+//     row traffic, not by instruction issue (profiles/ has the ncu evidence).
+// Arithmetic follows losses.py:4-12 on l2-normalised rows (base/initializers.py:26):
+//   pd = h^ + r^ - t^                      loss += w * log(1 + exp(|pd|^2))
+//   nd = e^ + r^ - t^ (head side) or h^ + r^ - e^ (tail side)   loss += log(1 + exp(-|nd|^2))
+// and accumulates d loss / d row into the gradient tables with red.global.add (vectorised).
+#include <cstdlib>
+#include "mke_rel.cuh"
+
+namespace mke {
+
+constexpr int kQPerWarp = 4;     // positives per warp
+constexpr int kPickStride = 33;  // MKE_MAX_NEG + 1: the four quarters of a warp hit distinct banks
+constexpr uint32_t kFull = 0xffffffffu;
+
+__device__ __forceinline__ float qsum(float v) {
+  v += __shfl_xor_sync(kFull, v, 4);
+  v += __shfl_xor_sync(kFull, v, 2);
+  v += __shfl_xor_sync(kFull, v, 1);
+  return v;
+}
+__device__ __forceinline__ void qsum3(float& a, float& b, float& c) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(kFull, a, o);
+    b += __shfl_xor_sync(kFull, b, o);
+    c += __shfl_xor_sync(kFull, c, o);
+  }
+}
+__device__ __forceinline__ void red_add_f2(float* p, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void red_add_f1(float* p, float x) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(x) : "memory");
+}
+
+// lane `sub` (0..7) of a quarter owns floats {32c + 4 sub .. +3 : c < FPL/4} and the FPL%4 floats
+// at 32 (FPL/4) + (FPL%4) sub of a row
+template <int FPL>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int sub, float (&x)[FPL]) {
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + c * 8 + sub);
+    x[4 * c] = v.x;
+    x[4 * c + 1] = v.y;
+    x[4 * c + 2] = v.z;
+    x[4 * c + 3] = v.w;
+  }
+  const float* tail = row + NV4 * 32 + REM * sub;
+  if constexpr (REM == 2) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(tail));
+    x[4 * NV4] = v.x;
+    x[4 * NV4 + 1] = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < REM; ++k) x[4 * NV4 + k] = __ldg(tail + k);
+  }
+}
+
+// grad_row += s * x
+template <int FPL>
+__device__ __forceinline__ void red_row(float* __restrict__ row, int sub, const float (&x)[FPL],
+                                        float s) {
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c)
+    red_add_f4(row + (c * 8 + sub) * 4,
+               make_float4(x[4 * c] * s, x[4 * c + 1] * s, x[4 * c + 2] * s, x[4 * c + 3] * s));
+  float* tail = row + NV4 * 32 + REM * sub;
+  if constexpr (REM == 2) {
+    red_add_f2(tail, x[4 * NV4] * s, x[4 * NV4 + 1] * s);
+  } else {
+#pragma unroll
+    for (int k = 0; k < REM; ++k) red_add_f1(tail + k, x[4 * NV4 + k] * s);
+  }
+}
+
+template <int FPL>
+__device__ __forceinline__ float sumsq(const float (&x)[FPL]) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < FPL; ++k) s = fmaf(x[k], x[k], s);
+  return s;
+}
+
+// ---- sampler, quarter layout --------------------------------------------------------------
+struct KgView {  // mke_kg_sampler_t selected per quarter (kg1 / kg2), held in registers
+  const int32_t* list;
+  const int32_t* neighbours;
+  mke_tripleset_t set;
+  int32_t base, n, n_nb;
+  __device__ __forceinline__ CandPool pool(int32_t anchor) const {
+    CandPool c;
+    if (neighbours != nullptr) {
+      const int32_t* row = neighbours + (size_t)anchor * (size_t)n_nb;
+      if (__ldg(row) >= 0) {
+        c.list = row;
+        c.base = 0;
+        c.n = (uint32_t)n_nb;
+        return c;
+      }
+    }
+    c.list = list;
+    c.base = base;
+    c.n = (uint32_t)n;
+    return c;
+  }
+};
+__device__ __forceinline__ KgView kg_view(const RelStepParams& p, bool first) {
+  KgView k;
+  k.list = first ? p.kg1.entity_list : p.kg2.entity_list;
+  k.neighbours = first ? p.kg1.neighbours : p.kg2.neighbours;
+  k.set.slots = first ? p.kg1.set.slots : p.kg2.set.slots;
+  k.set.capacity = first ? p.kg1.set.capacity : p.kg2.set.capacity;
+  k.base = first ? p.kg1.entity_base : p.kg2.entity_base;
+  k.n = first ? p.kg1.n_entities : p.kg2.n_entities;
+  k.n_nb = first ? p.kg1.n_neighbours : p.kg2.n_neighbours;
+  return k;
+}
+__device__ __forceinline__ uint32_t low_ones(int k) { return (k >= 32) ? kFull : ((1u << k) - 1u); }
+
+// generate_neg_triples_fast (base/batch.py:86-116) for ONE positive, executed by the 8 lanes of a
+// quarter with exactly the sequential semantics that oracle/device_sampler.py restates:
+//   per round (<= MKE_MAX_TRY): one head/tail coin; candidates c = 0, 1, 2, ... are drawn from the
+//   pool of the replaced entity and accepted unless they repeat an entity already accepted in this
+//   round (random.sample = without replacement) until `remaining` are accepted; accepted
+//   candidates that are known triples are dropped (not in the last round); stop at K.
+// Draws are counter based, so the 8 lanes evaluate candidates c_base + sub of a chunk at once
+// and ranks inside the chunk reproduce the sequential order.  All synchronisation is scoped to
+// the quarter (qmask): the four quarters of a warp may be in different rounds.
+// Writes pick[0..K) and returns the side mask (bit j: negative j replaces the head).
+__device__ __forceinline__ uint32_t sample_negs_quarter(const KgView& kg, int32_t h, int32_t r,
+                                                        int32_t t, int K, uint64_t skey, uint32_t i,
+                                                        int lane, volatile int32_t* pick) {
+  const int sub = lane & 7;
+  const int qshift = lane & 24;
+  const uint32_t qmask = 0xffu << qshift;
+  const uint32_t below = (1u << sub) - 1u;  // lower lanes of my quarter, after shifting to bit 0
+  int n_acc = 0, remaining = K;
+  uint32_t side_mask = 0;
+  for (uint32_t tr = 0; tr < MKE_MAX_TRY; ++tr) {
+    const bool head_side = (draw64(skey, i, tr, kSideDraw) >> 63) != 0;
+    const CandPool pool = kg.pool(head_side ? h : t);
+    // ---- draw: accept the first `remaining` candidates that do not repeat an accepted one ----
+    int np = 0;
+    for (uint32_t c_base = 0; np < remaining; c_base += 8) {
+      const uint32_t c = c_base + (uint32_t)sub;
+      const int32_t e = pool.at(draw_index(draw64(skey, i, tr, c), pool.n));
+      bool dup = false;
+      for (int k = 0; k < np; ++k) dup |= (pick[n_acc + k] == e);
+      const uint32_t same = (__match_any_sync(qmask, e) >> qshift) & 0xffu;
+      dup |= (same & below) != 0u;
+      dup = dup && (c + 1u < kSideDraw);
+      const uint32_t fresh = (__ballot_sync(qmask, !dup) >> qshift) & 0xffu;
+      const int rank = __popc(fresh & below);
+      __syncwarp(qmask);  // all lanes have compared against pick[] before it grows
+      if (!dup && np + rank < remaining) pick[n_acc + np + rank] = e;
+      __syncwarp(qmask);
+      np = min(remaining, np + __popc(fresh));
+    }
+    // ---- filter: drop known triples (the last round is accepted as is, batch.py:103-105) ------
+    int kept = np;
+    if (tr != MKE_MAX_TRY - 1) {
+      kept = 0;
+      for (int k0 = 0; k0 < np; k0 += 8) {
+        const int k = k0 + sub;
+        const int32_t e = pick[n_acc + (k < np ? k : 0)];
+        const uint64_t key = head_side ? triple_key(e, r, t) : triple_key(h, r, e);
+        const bool keep = (k < np) && !tripleset_contains(kg.set, key);
+        const uint32_t kb = (__ballot_sync(qmask, keep) >> qshift) & 0xffu;
+        // the ballot doubles as the barrier between reading pick[] above and compacting it
+        if (keep) pick[n_acc + kept + __popc(kb & below)] = e;
+        __syncwarp(qmask);
+        kept += __popc(kb);
+      }
+    }
+    if (head_side && kept > 0) side_mask |= low_ones(kept) << n_acc;
+    n_acc += kept;
+    if (n_acc >= K) break;
+    remaining = K - n_acc;
+  }
+  return side_mask;
+}
+
+// A negative whose side differs from the side of negative 0 of its positive (only possible when
+// rounds with different coins contributed, or in caller-supplied batches).  Rare: everything
+// is re-read from the tables and reduced straight into the gradient rows.  Executed by the whole
+// warp (shuffles use the full mask); quarters with on == false compute and discard.
+template <int FPL>
+static __device__ __noinline__ float odd_negative(const float* __restrict__ ent_var,
+                                                  const float* __restrict__ rel_var,
+                                                  float* __restrict__ ent_grad,
+                                                  float* __restrict__ rel_grad, int ent_norm,
+                                                  int rel_norm, int32_t h, int32_t r, int32_t t,
+                                                  int32_t e, bool head_side, bool on, int sub) {
+  constexpr int stride = FPL * 8;
+  float xh[FPL], xr[FPL], xt[FPL], xe[FPL];
+  load_row<FPL>(ent_var + (size_t)h * stride, sub, xh);
+  load_row<FPL>(rel_var + (size_t)r * stride, sub, xr);
+  load_row<FPL>(ent_var + (size_t)t * stride, sub, xt);
+  load_row<FPL>(ent_var + (size_t)e * stride, sub, xe);
+  float sh = sumsq<FPL>(xh), sr = sumsq<FPL>(xr), st = sumsq<FPL>(xt), se = sumsq<FPL>(xe);
+  qsum3(sh, sr, st);
+  se = qsum(se);
+  const float ih = ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
+  const float ir = rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
+  const float it = ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
+  const float ie = ent_norm ? rsqrtf(fmaxf(se, kNormEps)) : 1.f;
+  float nd[FPL], sn = 0.f;
+#pragma unroll
+  for (int k = 0; k < FPL; ++k) {
+    const float rr = xr[k] * ir;
+    nd[k] = head_side ? (fmaf(xe[k], ie, rr) - xt[k] * it) : (fmaf(xh[k], ih, rr) - xe[k] * ie);
+    sn = fmaf(nd[k], nd[k], sn);
+  }
+  sn = qsum(sn);
+  float lneg, sg;
+  softplus_sigmoid(-sn, lneg, sg);
+  if (!on) return 0.f;
+  const float cn = -2.f * sg;
+  red_row<FPL>(rel_grad + (size_t)r * stride, sub, nd, cn);
+  red_row<FPL>(ent_grad + (size_t)e * stride, sub, nd, head_side ? cn : -cn);
+  if (head_side)
+    red_row<FPL>(ent_grad + (size_t)t * stride, sub, nd, -cn);
+  else
+    red_row<FPL>(ent_grad + (size_t)h * stride, sub, nd, cn);
+  return lneg;
+}
+
+// ---- per-lane staging of rows in shared memory (cp.async / LDGSTS) --------------------------
+// A lane copies exactly the pieces of a row it will later read back, so no cross-lane
+// visibility is involved: cp.async.wait_group by the lane itself is the only synchronisation,
+// and no register is tied up while a row is in flight.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kSlots = 3;  // staging slots per lane: h, r, t rows, then a ring of negative rows
+
+// Warp staging area: [slot][16-byte chunk][lane] then [slot][lane] tails -> every LDS/LDGSTS of a
+// warp touches 32 consecutive pieces (conflict free).
+template <int FPL>
+struct Stage {
+  static constexpr int NV4 = FPL / 4, REM = FPL % 4;
+  static constexpr int kTailBase = kSlots * NV4 * 32 * 16;
+  static constexpr int kBytes = kTailBase + kSlots * 32 * REM * 4;
+  uint32_t base;  // shared-space address of this lane's first piece
+  int lane;
+  __device__ __forceinline__ uint32_t chunk(int slot, int c) const {
+    return base + ((slot * NV4 + c) * 32 + lane) * 16;
+  }
+  __device__ __forceinline__ uint32_t tail(int slot) const {
+    return base + kTailBase + (slot * 32 + lane) * (REM * 4);
+  }
+  __device__ __forceinline__ void issue(int slot, const float* __restrict__ row, int sub) const {
+#pragma unroll
+    for (int c = 0; c < NV4; ++c) cp_async16(chunk(slot, c), row + (c * 8 + sub) * 4);
+    const float* t = row + NV4 * 32 + REM * sub;
+    if constexpr (REM == 2) cp_async8(tail(slot), t);
+    if constexpr (REM == 1) cp_async4(tail(slot), t);
+    if constexpr (REM == 3) {
+      cp_async4(tail(slot), t);
+      cp_async4(tail(slot) + 4, t + 1);
+      cp_async4(tail(slot) + 8, t + 2);
+    }
+  }
+  __device__ __forceinline__ void read(int slot, float (&x)[FPL]) const {
+#pragma unroll
+    for (int c = 0; c < NV4; ++c) {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(chunk(slot, c)));
+      x[4 * c] = v.x;
+      x[4 * c + 1] = v.y;
+      x[4 * c + 2] = v.z;
+      x[4 * c + 3] = v.w;
+    }
+    if constexpr (REM == 2)
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x[4 * NV4]), "=f"(x[4 * NV4 + 1]) : "r"(tail(slot)));
+    if constexpr (REM == 1 || REM == 3) {
+#pragma unroll
+      for (int k = 0; k < REM; ++k)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[4 * NV4 + k]) : "r"(tail(slot) + 4 * k));
+    }
+  }
+};
+
+template <int FPL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelStepParams p) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr int stride = FPL * 8;
+  __shared__ __align__(16) unsigned char s_stage[WARPS][Stage<FPL>::kBytes];
+  __shared__ int32_t s_pick_all[WARPS][kQPerWarp][kPickStride];
+  __shared__ float s_loss[WARPS];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  const int q = lane >> 3;
+  const int wib = threadIdx.x >> 5;
+  volatile int32_t* pick = s_pick_all[wib][q];
+  Stage<FPL> stg;
+  stg.base = (uint32_t)__cvta_generic_to_shared(&s_stage[wib][0]);
+  stg.lane = lane;
+  const int n = p.len1 + p.len2;
+  const int K = p.K;
+  const int per_pass = gridDim.x * WARPS * kQPerWarp;
+  float loss_local = 0.f;
+
+  for (int i0 = (blockIdx.x * WARPS + wib) * kQPerWarp; i0 < n; i0 += per_pass) {
+    const int i = i0 + q;
+    const bool valid = i < n;
+    int32_t h = 0, r = 0, t = 0;
+    const bool first = i < p.len1;
+    if (valid) {
+      const int32_t* row = first ? p.pos1 + 3 * (size_t)i : p.pos2 + 3 * (size_t)(i - p.len1);
+      h = __ldg(row);
+      r = __ldg(row + 1);
+      t = __ldg(row + 2);
+    }
+    {
+      uint32_t side = 0u;
+      const bool active = valid;
+      // the three rows of the positive travel to shared memory while the sampler probes
+      stg.issue(0, p.ent_var + (size_t)h * stride, sub);
+      stg.issue(1, p.rel_var + (size_t)r * stride, sub);
+      stg.issue(2, p.ent_var + (size_t)t * stride, sub);
+      cp_async_commit();
+      if (K > 0) {
+        if (p.sampled) {
+          // idle quarters of the last warp sample from a harmless pool; nothing they draw is used
+          KgView kg = kg_view(p, valid ? first : (p.len1 > 0));
+          if (!valid || (p.dbg & 16)) {
+            kg.neighbours = nullptr;
+            kg.set.slots = nullptr;
+          }
+          side = sample_negs_quarter(kg, h, r, t, K, p.skey, (uint32_t)i, lane, pick);
+          if (!valid) {
+            side = 0u;
+            for (int c = sub; c < K; c += 8) pick[c] = 0;
+          }
+        } else {
+          for (int c = sub; c < K; c += 8) pick[c] = valid ? __ldg(p.neg_ent + (size_t)i * K + c) : 0;
+          side = valid ? __ldg(p.neg_side + i) : 0u;
+        }
+        __syncwarp();
+        if (p.neg_out != nullptr && active) {
+          for (int c = sub; c < K; c += 8) {
+            const bool hs = (side >> c) & 1u;
+            const int32_t e = pick[c];
+            int32_t* o = p.neg_out + ((size_t)i * K + c) * 3;
+            o[0] = hs ? e : h;
+            o[1] = r;
+            o[2] = hs ? t : e;
+          }
+        }
+      }
+      // ---- positive term -----------------------------------------------------------------
+      const bool side0 = (side & 1u) != 0u;  // side of negative 0: true = head replaced
+      const float sgn = side0 ? 1.f : -1.f;
+      float base[FPL], acc[FPL];
+      float bb = 0.f;  // |base|^2
+      {
+        float xh[FPL], xr[FPL], xt[FPL];
+        cp_async_wait<0>();
+        stg.read(0, xh);
+        stg.read(1, xr);
+        stg.read(2, xt);
+        float sh = sumsq<FPL>(xh), sr = sumsq<FPL>(xr), st = sumsq<FPL>(xt);
+        qsum3(sh, sr, st);
+        // the slots are free again (their contents fed the sums above): first negatives go out
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+          if (j < K) stg.issue(j, p.ent_var + (size_t)pick[j] * stride, sub);
+          cp_async_commit();
+        }
+        const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
+        const float ir = p.rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
+        const float it = p.ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
+        float sp = 0.f;
+#pragma unroll
+        for (int k = 0; k < FPL; ++k) {
+          const float hh = xh[k] * ih, tt = xt[k] * it;
+          const float pd = fmaf(xr[k], ir, hh) - tt;  // pos_distance (losses.py:5)
+          sp = fmaf(pd, pd, sp);
+          acc[k] = pd;
+          // head side: nd = e^ + (r^ - t^) = e^ + (pd - h^);  tail side: nd = (h^ + r^) - e^ = (pd + t^) - e^
+          base[k] = side0 ? (pd - hh) : (pd + tt);
+          bb = fmaf(base[k], base[k], bb);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          sp += __shfl_xor_sync(kFull, sp, o);
+          bb += __shfl_xor_sync(kFull, bb, o);
+        }
+        float lpos, sg;
+        softplus_sigmoid(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
+        const float wgt = (p.w != nullptr && active ? __ldg(p.w + i) : 1.f) * p.pos_scale;
+        if (active) loss_local += wgt * lpos;
+        const float cp = 2.f * sg * wgt;
+#pragma unroll
+        for (int k = 0; k < FPL; ++k) acc[k] *= cp;  // d loss / d pd; the K-loop adds the negatives
+        // the endpoint that no same-side negative shares gets its positive-term gradient now
+        if (active && !(p.dbg & 8)) red_row<FPL>(p.ent_grad + (size_t)(side0 ? h : t) * stride, sub, acc, sgn);
+      }
+      // ---- negatives: rows j+1, j+2 are in flight while row j is scored ------------------------
+      int slot = 0;
+      for (int j = 0; j < K; ++j) {
+        float x[FPL];
+        cp_async_wait<kSlots - 1>();
+        stg.read(slot, x);
+        const int32_t e = pick[j];
+        // |nd|^2 = |base + s ie e|^2 = |base|^2 + 2 s ie (base.e) + ie^2 (e.e): both dot products
+        // are reduced together, so a negative costs one shuffle chain instead of two
+        float ee = 0.f, be = 0.f;
+#pragma unroll
+        for (int k = 0; k < FPL; ++k) {
+          ee = fmaf(x[k], x[k], ee);
+          be = fmaf(x[k], base[k], be);
+        }
+        // slot is free: request row j + kSlots (the sums above consumed x)
+        if (j + kSlots < K) stg.issue(slot, p.ent_var + (size_t)pick[j + kSlots] * stride, sub);
+        cp_async_commit();
+        slot = (slot + 1 == kSlots) ? 0 : slot + 1;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          ee += __shfl_xor_sync(kFull, ee, o);
+          be += __shfl_xor_sync(kFull, be, o);
+        }
+        const float ie = p.ent_norm ? rsqrtf(fmaxf(ee, kNormEps)) : 1.f;
+        const float sie = sgn * ie;
+        const float sn = fmaf(ie * ie, ee, fmaf(2.f * sie, be, bb));  // -neg_score (losses.py:8)
+        float lneg, sg;
+        softplus_sigmoid(-sn, lneg, sg);  // log(1 + exp(neg_score)), neg_score = -sn
+        const bool odd = (((side >> j) & 1u) != 0u) != side0;
+        const bool on = active && !odd;
+        const float cn = on ? -2.f * sg : 0.f;
+        if (on) loss_local += lneg;
+#pragma unroll
+        for (int k = 0; k < FPL; ++k) {
+          x[k] = fmaf(x[k], sie, base[k]);  // neg_distance (losses.py:6)
+          acc[k] = fmaf(cn, x[k], acc[k]);
+        }
+        if (on && !(p.dbg & 8)) red_row<FPL>(p.ent_grad + (size_t)e * stride, sub, x, cn * sgn);
+      }
+      cp_async_wait<0>();
+      // ---- r gets every same-side term, the shared endpoint likewise -----------------------
+      if (active) {
+        if (!(p.dbg & 1)) red_row<FPL>(p.rel_grad + (size_t)r * stride, sub, acc, 1.f);
+        if (!(p.dbg & 8)) red_row<FPL>(p.ent_grad + (size_t)(side0 ? t : h) * stride, sub, acc, -sgn);
+        if (!(p.dbg & 2)) {
+        for (int c = sub; c < K; c += 8) p.ent_touched[pick[c]] = 1;
+        if (sub == 0) {
+          p.ent_touched[h] = 1;
+          p.ent_touched[t] = 1;
+          p.rel_touched[r] = 1;
+        }
+        }
+      }
+      // ---- negatives on the other side than negative 0 (rare), once base/acc are dead ------
+      const bool mixed = active && side != 0u && side != low_ones(K);
+      if (__any_sync(kFull, mixed)) {
+        for (int j = 1; j < K; ++j) {
+          const bool odd = active && ((((side >> j) & 1u) != 0u) != side0);
+          if (__any_sync(kFull, odd))
+            loss_local += odd_negative<FPL>(p.ent_var, p.rel_var, p.ent_grad, p.rel_grad, p.ent_norm,
+                                            p.rel_norm, h, r, t, pick[j], !side0, odd, sub);
+        }
+      }
+      __syncwarp();  // pick[] is rewritten by the next positive
+    }
+  }
+  // ---- loss: quarter leaders -> warp -> block -> one fp64 atomic ------------------------------
+  float v = (sub == 0) ? loss_local : 0.f;
+  v = warp_sum(v);
+  if (lane == 0) s_loss[wib] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) a += (double)s_loss[w];
+    if (a != 0.0 && !(p.dbg & 4)) atomicAdd(p.loss, a);
+  }
+}
+
+template <int FPL, int THREADS, int MINB>
+static int launch_q8(const RelStepParams& p, cudaStream_t stream) {
+  auto kern = rel_fused_q8_kernel<FPL, THREADS, MINB>;
+  constexpr int per_block = (THREADS / 32) * kQPerWarp;
+  const int n = p.len1 + p.len2;
+  static int per_sm_cached = 0;
+  if (per_sm_cached == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    per_sm_cached = per_sm;
+  }
+  const int full = sm_count() * per_sm_cached;
+  const int need = (n + per_block - 1) / per_block;
+  kern<<<need < full ? need : full, THREADS, 0, stream>>>(p);
+  MKE_CHECK_LAUNCH("rel_fused_q8_kernel");
+  return 0;
+}
+
+// strides with a quarter-warp instantiation: 32 (dim<=32), 64, 80 (dim 75), 104 (dim 100), 128
+int launch_rel_q8(const RelStepParams& p, cudaStream_t stream) {
+  static const int cfg = getenv("MKE_Q8_CFG") ? atoi(getenv("MKE_Q8_CFG")) : 0;  // tuning knob
+  switch (p.stride) {
+    case 32: return launch_q8<4, 64, 16>(p, stream);
+    case 64: return launch_q8<8, 64, 16>(p, stream);
+    case 80:
+      if (cfg == 1) return launch_q8<10, 64, 16>(p, stream);
+      if (cfg == 2) return launch_q8<10, 64, 20>(p, stream);
+      if (cfg == 3) return launch_q8<10, 128, 8>(p, stream);
+      return launch_q8<10, 64, 18>(p, stream);
+    case 104: return launch_q8<13, 64, 12>(p, stream);
+    case 128: return launch_q8<16, 64, 12>(p, stream);
+    default: return 1;
+  }
+}
+
+}  // namespace mke

@@ -8,16 +8,19 @@ namespace mke {
 
 __global__ void tripleset_build_kernel(mke_tripleset_t set, const int32_t* __restrict__ triples,
                                        int n) {
-  const uint64_t mask = set.capacity - 1;
+  const uint64_t mask = (set.capacity / kBucketSlots) - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint64_t key = triple_key(triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]);
-    uint64_t slot = mix64(key) & mask;
-    while (true) {
-      const unsigned long long prev =
-          atomicCAS(reinterpret_cast<unsigned long long*>(set.slots + slot),
-                    (unsigned long long)kEmptySlot, (unsigned long long)key);
-      if (prev == kEmptySlot || prev == key) break;
-      slot = (slot + 1) & mask;
+    uint64_t b = mix64(key) & mask;
+    bool done = false;
+    while (!done) {
+      unsigned long long* slot = reinterpret_cast<unsigned long long*>(set.slots + b * kBucketSlots);
+      for (int q = 0; q < kBucketSlots && !done; ++q) {  // front to back: buckets fill in order
+        const unsigned long long prev =
+            atomicCAS(slot + q, (unsigned long long)kEmptySlot, (unsigned long long)key);
+        done = (prev == kEmptySlot || prev == key);
+      }
+      b = (b + 1) & mask;
     }
   }
 }
@@ -61,8 +64,8 @@ __global__ void __launch_bounds__(kSampThreads)
 
 static int check_set(const mke_tripleset_t* set) {
   MKE_CHECK_ARG(set && set->slots, "null triple set");
-  MKE_CHECK_ARG(set->capacity >= 2 && (set->capacity & (set->capacity - 1)) == 0,
-                "triple-set capacity must be a power of two");
+  MKE_CHECK_ARG(set->capacity >= 8 && (set->capacity & (set->capacity - 1)) == 0,
+                "triple-set capacity must be a power of two >= 8");
   return 0;
 }
 

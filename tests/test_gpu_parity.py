@@ -28,8 +28,8 @@ def G():
     return gpu_util, tables
 
 
-CASES = [("relation_step_d75.npz", 0), ("relation_step_d75.npz", 1), ("relation_step_d128.npz", 0),
-         ("relation_step_d128.npz", 1)]
+# variant 0 = quarter-warp kernel (default), 1 = TMA bulk copy/reduce, 2 = warp-per-positive LDG/RED
+CASES = [(f, v) for f in ("relation_step_d75.npz", "relation_step_d128.npz") for v in (0, 1, 2)]
 
 
 @pytest.mark.parametrize("fname,variant", CASES)
@@ -99,7 +99,7 @@ def test_generic_triple_op_matches_golden(G, golden, fname):
     np.testing.assert_allclose(rel.raw(), g["rel1"], rtol=0, atol=ROW_ATOL)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_weighted_positives_only_variant(G, golden, variant):
     """ckgp graph (MultiKE_model.py:187-201): logistic_loss_wo_negs with weights, loss x2."""
     U, T = G
@@ -198,7 +198,7 @@ def test_device_sampler_bit_exact_vs_cpu_restatement(G, golden, mode):
         assert np.array_equal(got, want)  # index work: bit-exact
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_fused_sampled_step_equals_sampler_plus_structured(G, golden, variant):
     """The fused kernel draws exactly what mke_sample_uniform / the CPU restatement draw, and
     scores them exactly like the structured path."""
@@ -268,7 +268,7 @@ def test_empty_and_ragged_batches(G, golden):
     acc = T.new_loss_accumulator()
     T.rel_step_sampled(ent, rel, t1[:0], dk1, t2[:0], dk2, 10, 1, 0, acc)
     assert U.loss_value(acc) == 0.0 and float(ent.grad.abs().max()) == 0.0
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         a = T.new_loss_accumulator()
         T.rel_step_sampled(ent, rel, t1[:0], dk1, t2[:7], dk2, 10, 1, 0, a, variant=variant)   # kg1 exhausted
         T.rel_step_sampled(ent, rel, t1[:1], dk1, None, None, 10, 1, 1, a, variant=variant)
@@ -296,7 +296,7 @@ def full(G):
     return kgs, ent0, rel0, kg1, kg2
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_full_size_step_vs_dense_torch_and_properties(G, full, variant):
     U, T = G
     kgs, ent0, rel0, kg1, kg2 = full
@@ -355,7 +355,7 @@ def test_full_size_linearity_and_variant_agreement(G, full):
     K, B1, B2 = 10, 10159, 9841
     p1, p2 = kgs["triples1"][B1:2 * B1], kgs["triples2"][B2:2 * B2]
     outs = []
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ent, rel = U.make_tables(ent0.numpy(), rel0.numpy())
         acc = T.new_loss_accumulator()
         T.rel_step_sampled(ent, rel, p1, kg1, p2, kg2, K, 7, 3, acc, variant=variant)
@@ -364,9 +364,10 @@ def test_full_size_linearity_and_variant_agreement(G, full):
             T.rel_step_sampled(ent, rel, p1, kg1, p2, kg2, K, 7, 3, acc, variant=variant)
             assert U.loss_value(acc) == pytest.approx(2 * outs[0][0], rel=1e-6)
             torch.testing.assert_close(ent.grad, 2 * outs[0][1], rtol=1e-4, atol=1e-5)
-    assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6)
-    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-4, atol=2e-5)
-    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-4, atol=2e-4)
+    for other in outs[1:]:
+        assert outs[0][0] == pytest.approx(other[0], rel=1e-6)
+        torch.testing.assert_close(outs[0][1], other[1], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(outs[0][2], other[2], rtol=1e-4, atol=2e-4)
     # generic op on the sampled negatives
     neg = T.sample_uniform(p1, kg1, p2, kg2, K, 7, 3)
     ent, rel = U.make_tables(ent0.numpy(), rel0.numpy())
