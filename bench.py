@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=int(os.environ.get("MKE_VARIANT", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="draw negatives inside the fused kernel")
     ap.add_argument("--cpu-steps", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -177,7 +178,8 @@ def main():
     K, dim, B = w["neg"], w["dim"], w["batch"]
     gen = torch.Generator().manual_seed(20190754 + rank)
     rv = RelationView(kgs["n_ent"], kgs["n_rel"], dim, kgs["triples1"], kgs["triples2"], kgs["ent_split"],
-                      batch_size=B, neg_num=K, lr=0.001, seed=1234 + rank, variant=args.variant, generator=gen)
+                      batch_size=B, neg_num=K, lr=0.001, seed=1234 + rank, variant=args.variant, generator=gen,
+                      pipelined=not args.no_pipeline)
     spe = rv.triple_steps
     warmup = max(args.warmup, 3)
 
@@ -189,7 +191,7 @@ def main():
     # ---- device-resident leg ---------------------------------------------------------------
     step_no = 0
     for _ in range(warmup):
-        rv.step_resident(step_no % spe)
+        rv.step_resident(step_no % spe, (step_no + 1) % spe)
         step_no += 1
     clocks = ClockSampler(local_rank)
     barrier()
@@ -201,7 +203,7 @@ def main():
     positives = 0
     e0.record()
     for _ in range(args.steps):
-        positives += rv.step_resident(step_no % spe)
+        positives += rv.step_resident(step_no % spe, (step_no + 1) % spe)
         step_no += 1
     e1.record()
     barrier()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MKE_ABI_VERSION 1
+#define MKE_ABI_VERSION 2
 #define MKE_EINVAL (-100000)
 #define MKE_MAX_NEG 32        /* K (negatives per positive) supported by the fused kernel */
 #define MKE_MAX_TRY 10        /* base/batch.py:86 max_try=10 */
@@ -42,11 +42,19 @@ typedef struct mke_table {
   float*   var;        /* [rows, stride] raw variable V (NOT normalised)                       */
   float*   grad;       /* [rows, stride] dLoss/dE accumulator, E = l2_normalize(V,1) if
                           normalised else V; all-zero between steps; NULL => constant table     */
-  uint8_t* touched;    /* [rows] 1 if grad row may be non-zero; all-zero between steps          */
+  uint8_t* touched;    /* [rows] 1 if grad row may be non-zero; all-zero between steps.  NULL =>
+                          no flags: phase 2 visits every row (right for small tables such as
+                          rel_embeds / attr_embeds, whose hot rows would make the flag byte a
+                          contended store target)                                                */
   int32_t  rows;
   int32_t  stride;     /* floats per row, multiple of 4                                         */
   int32_t  dim;        /* logical embedding dimension (<= stride)                               */
   int32_t  normalised; /* 1: the model reads l2_normalize(var,1) (is_l2_norm=True)              */
+  int32_t  grad_replicas; /* 0/1: grad is [rows, stride].  R > 1: grad is [R, rows, stride]; phase 1
+                          spreads its reductions over the R copies (a thread block adds into
+                          copy blockIdx % R) and phase 2 sums and re-zeroes them.  For small hot
+                          tables (rel_embeds: the top relation carries 10-16 % of a batch), where
+                          thousands of reductions per step would otherwise serialise on one row  */
 } mke_table_t;
 
 /*
@@ -143,6 +151,14 @@ int mke_rel_step_structured(const mke_table_t* ent, const mke_table_t* rel,
                             const float* w_or_null, float pos_scale,
                             double* loss_accum, int32_t variant, mke_stream_t stream);
 
+/* The same for a batch given as a kg1 slice followed by a kg2 slice (base/batch.py:33-42);
+ * neg_ent / neg_side are indexed by the position in the concatenated batch. */
+int mke_rel_step_structured2(const mke_table_t* ent, const mke_table_t* rel,
+                             const int32_t* pos1, int32_t len1, const int32_t* pos2, int32_t len2,
+                             int32_t K, const int32_t* neg_ent, const uint32_t* neg_side,
+                             const float* w_or_null, float pos_scale,
+                             double* loss_accum, int32_t variant, mke_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Phase 2: optimizer.
  * ------------------------------------------------------------------------------------------ */
@@ -158,6 +174,14 @@ int mke_rel_step_structured(const mke_table_t* ent, const mke_table_t* rel,
  * ([rows,stride], initial value 0.1): the reference creates one per generate_optimizer call.
  */
 int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, float lr, mke_stream_t stream);
+
+/*
+ * The same for two tables in ONE launch when their strides agree (the entity and the relation
+ * table of a view: both appear in every generate_optimizer var list, MultiKE_model.py:30);
+ * otherwise two launches.  Each table keeps its own accumulator slot and learning rate.
+ */
+int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
+                                const mke_table_t* b, float* acc_b, float lr_b, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Sampler pieces (base/batch.py:86-116, attr_batch.py:13-25) usable on their own.
@@ -178,6 +202,17 @@ int mke_sample_uniform(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t
                        const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
                        int32_t K, uint64_t seed, uint64_t step, int32_t* neg_out,
                        mke_stream_t stream);
+
+/*
+ * The same draws in the structured form mke_rel_step_structured consumes: neg_ent [(len1+len2), K]
+ * int32 (corrupted entity of negative j) and neg_side [(len1+len2)] (bit j set: negative j
+ * replaces the head).  Sampling reads no embedding table, so a driver can run it for step s+1 on
+ * a second stream while step s trains (multike_b200/relation_view.py does).
+ */
+int mke_sample_structured(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                          const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                          int32_t K, uint64_t seed, uint64_t step, int32_t* neg_ent,
+                          uint32_t* neg_side, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Table utilities.

@@ -11,7 +11,7 @@ from . import build as _build
 
 _c = ctypes
 c_i32p = _c.c_void_p  # device pointers travel as integers
-MKE_ABI_VERSION = 1
+MKE_ABI_VERSION = 2
 MKE_EINVAL = -100000
 MKE_MAX_NEG = 32
 MKE_MAX_TRY = 10
@@ -26,6 +26,7 @@ class MkeTable(_c.Structure):
         ("stride", _c.c_int32),
         ("dim", _c.c_int32),
         ("normalised", _c.c_int32),
+        ("grad_replicas", _c.c_int32),
     ]
 
 
@@ -58,10 +59,13 @@ SIGNATURES = {
     "mke_rel_step_sampled": (_i32, [_PT, _PT, _vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp,
                                     _f32, _vp, _vp, _i32, _vp]),
     "mke_rel_step_structured": (_i32, [_PT, _PT, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
+    "mke_rel_step_structured2": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rows_apply_adagrad": (_i32, [_PT, _vp, _f32, _vp]),
+    "mke_rows_apply_adagrad_pair": (_i32, [_PT, _vp, _f32, _PT, _vp, _f32, _vp]),
     "mke_tripleset_build": (_i32, [_PS, _vp, _i32, _vp]),
     "mke_tripleset_contains": (_i32, [_PS, _vp, _i32, _vp, _vp]),
     "mke_sample_uniform": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp]),
+    "mke_sample_structured": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp, _vp]),
     "mke_table_export": (_i32, [_PT, _vp, _i32, _vp, _vp]),
     "mke_fill_rows": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp]),
 }

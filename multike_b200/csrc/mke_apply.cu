@@ -15,15 +15,15 @@ template <int NV>
 __global__ void __launch_bounds__(kApplyThreads)
     apply_adagrad_kernel(float* __restrict__ var, float* __restrict__ grad,
                          uint8_t* __restrict__ touched, float* __restrict__ acc, int rows,
-                         int stride, int nchunk, int normalised, float lr) {
+                         int stride, int nchunk, int normalised, float lr, int replicas) {
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * kApplyWarps + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * kApplyWarps;
   for (int base = gwarp * 32; base < rows; base += nwarps * 32) {
     const int my = base + lane;
-    const bool flag = (my < rows) && (touched[my] != 0);
+    const bool flag = (my < rows) && (touched == nullptr || touched[my] != 0);
     uint32_t m = __ballot_sync(0xffffffffu, flag);
-    if (flag) touched[my] = 0;
+    if (flag && touched != nullptr) touched[my] = 0;
     while (m) {
       const int row = base + (__ffs(m) - 1);
       m &= m - 1;
@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(kApplyThreads)
         const int c = lane + 32 * q;
         if (c < nchunk) {
           g[q] = *reinterpret_cast<const float4*>(pg + 4 * c);
+          for (int rep = 1; rep < replicas; ++rep)
+            g[q] = f4_add(g[q], *reinterpret_cast<const float4*>(pg + (size_t)rep * rows * stride + 4 * c));
           v[q] = *reinterpret_cast<const float4*>(pv + 4 * c);
           a[q] = *reinterpret_cast<const float4*>(pa + 4 * c);
         } else {
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(kApplyThreads)
           v[q].w -= gv.w * lr * (a[q].w > 0.f ? rsqrtf(a[q].w) : 0.f);
           *reinterpret_cast<float4*>(pv + 4 * c) = v[q];
           *reinterpret_cast<float4*>(pa + 4 * c) = a[q];
-          *reinterpret_cast<float4*>(pg + 4 * c) = f4_zero();
+          for (int rep = 0; rep < replicas; ++rep)
+            *reinterpret_cast<float4*>(pg + (size_t)rep * rows * stride + 4 * c) = f4_zero();
         }
       }
     }
@@ -81,10 +84,10 @@ __global__ void __launch_bounds__(kApplyThreads)
 }
 
 // ---- quarter-warp layout (default for strides 32/64/80/104/128) -------------------------------
-// A warp scans 32 flag bytes, then its four quarters take four flagged rows at a time; lane
-// `sub` of a quarter owns FPL = stride/8 floats of the row (same layout as mke_rel_q8.cu), so the
-// three reads and three writes of a row are full 128-byte segments and two 3-step shuffle
-// reductions replace the 5-step warp ones.  All 9 loads of a row are issued before first use.
+// Lane `sub` of a quarter owns FPL = stride/8 floats of a row (same layout as mke_rel_q8.cu), so
+// the three reads and three writes of a row are full 128-byte segments and one 3-step shuffle
+// reduction of two values replaces two 5-step warp ones.  All loads of a row are issued before
+// first use.
 constexpr uint32_t kFullMask = 0xffffffffu;
 
 template <int FPL>
@@ -120,23 +123,91 @@ __device__ __forceinline__ void q_store(float* __restrict__ row, int sub, const 
   }
 }
 
-template <int FPL, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-    apply_adagrad_q8_kernel(float* __restrict__ var, float* __restrict__ grad,
-                            uint8_t* __restrict__ touched, float* __restrict__ acc, int rows,
-                            int normalised, float lr) {
-  constexpr int WARPS = THREADS / 32;
+struct ApplyTable {
+  float* var;
+  float* grad;
+  uint8_t* touched;
+  float* acc;
+  int rows;
+  int normalised;
+  float lr;
+  int replicas;  // gradient copies to sum and re-zero (mke_table_t.grad_replicas), >= 1
+};
+static ApplyTable apply_table(const mke_table_t* t, float* acc, float lr) {
+  return ApplyTable{t->var, t->grad, t->touched, acc, t->rows, t->normalised, lr,
+                    t->grad_replicas > 1 ? t->grad_replicas : 1};
+}
+
+// Normalise-backward + Adagrad for the row at float offset `off`, executed by a quarter (lanes with
+// on == false run along for the shuffles and write nothing).
+template <int FPL>
+__device__ __forceinline__ void apply_one_row(const ApplyTable& T, size_t off, bool on, int sub) {
   constexpr int stride = FPL * 8;
-  const int lane = threadIdx.x & 31;
+  const size_t rep_floats = (size_t)T.rows * stride;
+  float g[FPL], v[FPL], a[FPL];
+  q_load<FPL>(T.grad + off, sub, g);
+  q_load<FPL>(T.var + off, sub, v);
+  q_load<FPL>(T.acc + off, sub, a);
+  // gradient copies of small hot tables (mke_table_t.grad_replicas)
+  for (int rep = 1; rep < T.replicas; ++rep) {
+    float g2[FPL];
+    q_load<FPL>(T.grad + rep * rep_floats + off, sub, g2);
+#pragma unroll
+    for (int k = 0; k < FPL; ++k) g[k] += g2[k];
+  }
+  float inv = 1.f, coef = 0.f;
+  if (T.normalised) {
+    float ss = 0.f, vg = 0.f;
+#pragma unroll
+    for (int k = 0; k < FPL; ++k) {
+      ss = fmaf(v[k], v[k], ss);
+      vg = fmaf(v[k], g[k], vg);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(kFullMask, ss, o);
+      vg += __shfl_xor_sync(kFullMask, vg, o);
+    }
+    // y = v * rsqrt(max(|v|^2, eps)); the max() routes no gradient to |v|^2 below eps
+    inv = rsqrtf(fmaxf(ss, kNormEps));
+    coef = (ss >= kNormEps) ? vg * inv * inv : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < FPL; ++k) {
+    const float gv = (g[k] - v[k] * coef) * inv;
+    a[k] = fmaf(gv, gv, a[k]);
+    // var -= grad * lr * rsqrt(accum)   (ApplyAdagrad, no epsilon) [TF semantics]
+    v[k] -= gv * T.lr * (a[k] > 0.f ? rsqrtf(a[k]) : 0.f);
+    g[k] = 0.f;
+  }
+  if (on) {
+    q_store<FPL>(T.var + off, sub, v);
+    q_store<FPL>(T.acc + off, sub, a);
+    for (int rep = 0; rep < T.replicas; ++rep) q_store<FPL>(T.grad + rep * rep_floats + off, sub, g);
+  }
+}
+
+// Large tables: a warp scans 32 flag bytes, then its four quarters take four flagged rows at a
+// time (flagged rows are compacted by ballot, so all quarters stay busy whatever the touched
+// fraction is).  Small tables (no flags): one row per quarter, every row.
+template <int FPL>
+__device__ __forceinline__ void apply_rows(const ApplyTable& T, int gwarp, int nwarps, int lane) {
+  constexpr int stride = FPL * 8;
   const int sub = lane & 7;
   const int q = lane >> 3;
-  const int gwarp = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * WARPS;
-  for (int base = gwarp * 32; base < rows; base += nwarps * 32) {
+  if (T.touched == nullptr) {
+    for (int r0 = gwarp * 4; r0 < T.rows; r0 += nwarps * 4) {
+      const int row = r0 + q;
+      const bool on = row < T.rows;
+      apply_one_row<FPL>(T, (size_t)(on ? row : 0) * stride, on, sub);
+    }
+    return;
+  }
+  for (int base = gwarp * 32; base < T.rows; base += nwarps * 32) {
     const int my = base + lane;
-    const bool flag = (my < rows) && (touched[my] != 0);
+    const bool flag = (my < T.rows) && (T.touched[my] != 0);
     uint32_t m = __ballot_sync(kFullMask, flag);
-    if (flag) touched[my] = 0;
+    if (flag) T.touched[my] = 0;
     while (m) {  // warp-uniform
       // quarter q takes the q-th lowest flagged row of the remaining ones
       uint32_t mm = m;
@@ -149,47 +220,27 @@ __global__ void __launch_bounds__(THREADS, MINB)
       }
       m = mm;
       const bool on = bit >= 0;
-      const size_t off = (size_t)(base + (on ? bit : 0)) * stride;
-      float g[FPL], v[FPL], a[FPL];
-      q_load<FPL>(grad + off, sub, g);
-      q_load<FPL>(var + off, sub, v);
-      q_load<FPL>(acc + off, sub, a);
-      float inv = 1.f, coef = 0.f;
-      if (normalised) {
-        float ss = 0.f, vg = 0.f;
-#pragma unroll
-        for (int k = 0; k < FPL; ++k) {
-          ss = fmaf(v[k], v[k], ss);
-          vg = fmaf(v[k], g[k], vg);
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-          ss += __shfl_xor_sync(kFullMask, ss, o);
-          vg += __shfl_xor_sync(kFullMask, vg, o);
-        }
-        // y = v * rsqrt(max(|v|^2, eps)); the max() routes no gradient to |v|^2 below eps
-        inv = rsqrtf(fmaxf(ss, kNormEps));
-        coef = (ss >= kNormEps) ? vg * inv * inv : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < FPL; ++k) {
-        const float gv = (g[k] - v[k] * coef) * inv;
-        a[k] = fmaf(gv, gv, a[k]);
-        // var -= grad * lr * rsqrt(accum)   (ApplyAdagrad, no epsilon) [TF semantics]
-        v[k] -= gv * lr * (a[k] > 0.f ? rsqrtf(a[k]) : 0.f);
-        g[k] = 0.f;
-      }
-      if (on) {
-        q_store<FPL>(var + off, sub, v);
-        q_store<FPL>(acc + off, sub, a);
-        q_store<FPL>(grad + off, sub, g);
-      }
+      apply_one_row<FPL>(T, (size_t)(base + (on ? bit : 0)) * stride, on, sub);
     }
   }
 }
 
+// Up to two tables of equal stride in one launch (the entity and the relation table of a view):
+// the first blocks_a thread blocks sweep table A, the others table B, concurrently.
 template <int FPL, int THREADS, int MINB>
-static int launch_apply_q8(const mke_table_t* t, float* acc, float lr, cudaStream_t stream) {
+__global__ void __launch_bounds__(THREADS, MINB)
+    apply_adagrad_q8_kernel(const ApplyTable A, const ApplyTable B, int blocks_a) {
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  if ((int)blockIdx.x < blocks_a)
+    apply_rows<FPL>(A, blockIdx.x * WARPS + wib, blocks_a * WARPS, lane);
+  else
+    apply_rows<FPL>(B, (blockIdx.x - blocks_a) * WARPS + wib, (gridDim.x - blocks_a) * WARPS, lane);
+}
+
+template <int FPL, int THREADS, int MINB>
+static int launch_apply_q8(const ApplyTable& A, const ApplyTable& B, cudaStream_t stream) {
   auto kern = apply_adagrad_q8_kernel<FPL, THREADS, MINB>;
   constexpr int WARPS = THREADS / 32;
   static int per_sm_cached = 0;
@@ -200,12 +251,29 @@ static int launch_apply_q8(const mke_table_t* t, float* acc, float lr, cudaStrea
     per_sm_cached = per_sm;
   }
   const int full = sm_count() * per_sm_cached;
-  int need = ((t->rows + 31) / 32 + WARPS - 1) / WARPS;
-  if (need > full) need = full;
-  if (need < 1) need = 1;
-  kern<<<need, THREADS, 0, stream>>>(t->var, t->grad, t->touched, acc, t->rows, t->normalised, lr);
+  auto blocks_for = [&](const ApplyTable& T) {
+    const int rows_per_warp = T.touched ? 32 : 4;
+    int need = ((T.rows + rows_per_warp - 1) / rows_per_warp + WARPS - 1) / WARPS;
+    return need > full ? full : need;
+  };
+  const int ba = A.rows > 0 ? blocks_for(A) : 0;
+  const int bb = B.rows > 0 ? blocks_for(B) : 0;
+  if (ba + bb < 1) return 0;
+  kern<<<ba + bb, THREADS, 0, stream>>>(A, B, ba);
   MKE_CHECK_LAUNCH("apply_adagrad_q8_kernel");
   return 0;
+}
+
+// returns 1 when the stride has no quarter-warp instantiation
+static int dispatch_apply_q8(int stride, const ApplyTable& A, const ApplyTable& B, cudaStream_t s) {
+  switch (stride) {
+    case 32: return launch_apply_q8<4, 128, 12>(A, B, s);
+    case 64: return launch_apply_q8<8, 128, 10>(A, B, s);
+    case 80: return launch_apply_q8<10, 128, 6>(A, B, s);
+    case 104: return launch_apply_q8<13, 128, 8>(A, B, s);
+    case 128: return launch_apply_q8<16, 128, 6>(A, B, s);
+    default: return 1;
+  }
 }
 
 template <int NV>
@@ -220,7 +288,8 @@ static int launch_apply(const mke_table_t* t, float* acc, float lr, cudaStream_t
   if (need > full) need = full;
   if (need < 1) need = 1;
   kern<<<need, kApplyThreads, 0, stream>>>(t->var, t->grad, t->touched, acc, t->rows, t->stride,
-                                           (t->dim + 3) / 4, t->normalised, lr);
+                                           (t->dim + 3) / 4, t->normalised, lr,
+                                           t->grad_replicas > 1 ? t->grad_replicas : 1);
   MKE_CHECK_LAUNCH("apply_adagrad_kernel");
   return 0;
 }
@@ -231,8 +300,7 @@ using namespace mke;
 
 extern "C" int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, float lr,
                                       mke_stream_t stream) {
-  MKE_CHECK_ARG(table && table->var && table->grad && table->touched && acc,
-                "apply needs var/grad/touched/acc");
+  MKE_CHECK_ARG(table && table->var && table->grad && acc, "apply needs var/grad/acc");
   MKE_CHECK_ARG(table->stride % 4 == 0 && table->dim <= table->stride && table->dim > 0,
                 "bad stride/dim");
   if (table->rows <= 0) return 0;
@@ -241,14 +309,10 @@ extern "C" int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, floa
   cudaStream_t s = (cudaStream_t)stream;
   static const int generic = getenv("MKE_APPLY_GENERIC") ? atoi(getenv("MKE_APPLY_GENERIC")) : 0;
   if (!generic) {
-    switch (table->stride) {
-      case 32: return launch_apply_q8<4, 128, 12>(table, acc, lr, s);
-      case 64: return launch_apply_q8<8, 128, 10>(table, acc, lr, s);
-      case 80: return launch_apply_q8<10, 128, 8>(table, acc, lr, s);
-      case 104: return launch_apply_q8<13, 128, 8>(table, acc, lr, s);
-      case 128: return launch_apply_q8<16, 128, 6>(table, acc, lr, s);
-      default: break;
-    }
+    const ApplyTable A = apply_table(table, acc, lr);
+    const ApplyTable B{nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f, 1};
+    const int rc = dispatch_apply_q8(table->stride, A, B, s);
+    if (rc <= 0) return rc;
   }
   switch (nv) {
     case 1: return launch_apply<1>(table, acc, lr, s);
@@ -256,4 +320,20 @@ extern "C" int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, floa
     case 3: case 4: return launch_apply<4>(table, acc, lr, s);
     default: return launch_apply<8>(table, acc, lr, s);
   }
+}
+
+extern "C" int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
+                                           const mke_table_t* b, float* acc_b, float lr_b,
+                                           mke_stream_t stream) {
+  MKE_CHECK_ARG(a && b, "null table");
+  if (a->stride == b->stride && a->var && a->grad && acc_a && b->var && b->grad && acc_b &&
+      a->rows > 0 && b->rows > 0 &&
+      (int64_t)a->rows + (int64_t)b->rows < (1ll << 31)) {
+    const ApplyTable A = apply_table(a, acc_a, lr_a);
+    const ApplyTable B = apply_table(b, acc_b, lr_b);
+    const int rc = dispatch_apply_q8(a->stride, A, B, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
+  if (int rc = mke_rows_apply_adagrad(a, acc_a, lr_a, stream)) return rc;
+  return mke_rows_apply_adagrad(b, acc_b, lr_b, stream);
 }

@@ -113,21 +113,46 @@ __device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
                : "memory");
 }
 
+// Row flag for phase 2: a plain fire-and-forget byte store.  (Test-before-set was measured and is
+// worse: the flag load joins the warp's dependent chain; hot small tables carry no flags at all.)
+__device__ __forceinline__ void mark_touched(uint8_t* __restrict__ flags, int32_t row) {
+  if (flags != nullptr) flags[row] = 1;
+}
+
 // Triple set: open addressing over BUCKETS of four 64-bit keys (one 32-byte sector); a bucket
 // fills front to back and never empties, so a lookup reads one sector and stops at the first
 // bucket whose last slot is still empty.  A miss costs one memory round trip at load <= 0.5.
 constexpr int kBucketSlots = 4;
-__device__ __forceinline__ bool tripleset_contains(const mke_tripleset_t& s, uint64_t key) {
-  if (s.slots == nullptr) return false;
+// continue a lookup at bucket b (buckets before b were full and did not hold the key)
+__device__ __forceinline__ bool tripleset_probe_from(const mke_tripleset_t& s, uint64_t key, uint64_t b) {
   const uint64_t mask = (s.capacity / kBucketSlots) - 1;
-  uint64_t b = mix64(key) & mask;
   while (true) {
+    b &= mask;
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(s.slots + b * kBucketSlots);
     const ulonglong2 lo = __ldg(p), hi = __ldg(p + 1);
     if (lo.x == key || lo.y == key || hi.x == key || hi.y == key) return true;
     if (hi.y == kEmptySlot) return false;
-    b = (b + 1) & mask;
+    ++b;
   }
+}
+__device__ __forceinline__ bool tripleset_contains(const mke_tripleset_t& s, uint64_t key) {
+  if (s.slots == nullptr) return false;
+  return tripleset_probe_from(s, key, mix64(key));
+}
+// two independent lookups with both sectors in flight at once
+__device__ __forceinline__ void tripleset_contains2(const mke_tripleset_t& s, uint64_t k0, uint64_t k1,
+                                                    bool& in0, bool& in1) {
+  in0 = in1 = false;
+  if (s.slots == nullptr) return;
+  const uint64_t mask = (s.capacity / kBucketSlots) - 1;
+  const uint64_t b0 = mix64(k0) & mask, b1 = mix64(k1) & mask;
+  const ulonglong2* p0 = reinterpret_cast<const ulonglong2*>(s.slots + b0 * kBucketSlots);
+  const ulonglong2* p1 = reinterpret_cast<const ulonglong2*>(s.slots + b1 * kBucketSlots);
+  const ulonglong2 a0 = __ldg(p0), a1 = __ldg(p0 + 1), c0 = __ldg(p1), c1 = __ldg(p1 + 1);
+  in0 = (a0.x == k0 || a0.y == k0 || a1.x == k0 || a1.y == k0);
+  in1 = (c0.x == k1 || c0.y == k1 || c1.x == k1 || c1.y == k1);
+  if (!in0 && a1.y != kEmptySlot) in0 = tripleset_probe_from(s, k0, b0 + 1);  // full bucket: rare
+  if (!in1 && c1.y != kEmptySlot) in1 = tripleset_probe_from(s, k1, b1 + 1);
 }
 
 // candidate pool for replacing `anchor` (base/batch.py:93-94 neighbor.get(e, entities_list))

@@ -9,6 +9,7 @@
 //              SASS UBLKCP) and gradient rows returned with cp.reduce.async.bulk .add.f32
 //              (SASS UBLKRED) -- one bulk op per 300-byte row instead of 19 lanes of LSU work.
 // The arithmetic is identical in both; DESIGN.md has the measurements behind the default.
+#include <cstdio>
 #include <cstdlib>
 #include "mke_rel.cuh"
 
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kRelThreads) rel_fused_ldg_kernel(const RelSte
     // h += gp + A ; t -= gp + B ; r += gp + A + B
     float* gh = p.ent_grad + (size_t)h * p.stride;
     float* gt = p.ent_grad + (size_t)t * p.stride;
-    float* gr = p.rel_grad + (size_t)r * p.stride;
+    float* gr = rel_grad_replica(p) + (size_t)r * p.stride;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       if (act[v]) {
@@ -195,11 +196,11 @@ __global__ void __launch_bounds__(kRelThreads) rel_fused_ldg_kernel(const RelSte
         red_add_f4(gr + off[v], f4_add(a, accB[v]));
       }
     }
-    if (lane < p.K) p.ent_touched[e] = 1;
+    if (lane < p.K) mark_touched(p.ent_touched, e);
     if (lane == 0) {
-      p.ent_touched[h] = 1;
-      p.ent_touched[t] = 1;
-      p.rel_touched[r] = 1;
+      mark_touched(p.ent_touched, h);
+      mark_touched(p.ent_touched, t);
+      mark_touched(p.rel_touched, r);
     }
   }
   block_loss_commit(loss_local, p.loss);
@@ -430,9 +431,9 @@ __global__ void __launch_bounds__(kTmaThreads) rel_fused_tma_kernel(const RelSte
       bool is_rel;
       row_owner(cur, row, is_rel);
       if (lane < rows) {
-        float* dst = (is_rel ? p.rel_grad : p.ent_grad) + (size_t)row * p.stride;
+        float* dst = (is_rel ? rel_grad_replica(p) : p.ent_grad) + (size_t)row * p.stride;
         bulk_red_add_s2g(dst, smem_u32(out + (size_t)lane * p.stride), data_bytes);
-        (is_rel ? p.rel_touched : p.ent_touched)[row] = 1;
+        mark_touched(is_rel ? p.rel_touched : p.ent_touched, row);
       }
       bulk_commit();
     }
@@ -455,13 +456,14 @@ __global__ void __launch_bounds__(kTmaThreads) rel_fused_tma_kernel(const RelSte
 // --------------------------------------------------------------------------------------------
 static int validate_tables(const mke_table_t* ent, const mke_table_t* rel) {
   MKE_CHECK_ARG(ent && rel, "null table");
-  MKE_CHECK_ARG(ent->var && ent->grad && ent->touched, "entity table needs var/grad/touched");
-  MKE_CHECK_ARG(rel->var && rel->grad && rel->touched, "relation table needs var/grad/touched");
+  MKE_CHECK_ARG(ent->var && ent->grad, "entity table needs var/grad");
+  MKE_CHECK_ARG(rel->var && rel->grad, "relation table needs var/grad");
   MKE_CHECK_ARG(ent->stride == rel->stride && ent->dim == rel->dim,
                 "fused relation kernel needs equal dim/stride for both tables (%d/%d vs %d/%d)",
                 ent->dim, ent->stride, rel->dim, rel->stride);
   MKE_CHECK_ARG(ent->stride % 4 == 0 && ent->dim <= ent->stride && ent->dim > 0, "bad stride/dim");
   MKE_CHECK_ARG(ent->stride <= 256, "fused relation kernel supports stride <= 256 floats");
+  MKE_CHECK_ARG(ent->grad_replicas <= 1, "the entity table of the fused relation kernel takes no gradient replicas");
   return 0;
 }
 
@@ -479,6 +481,31 @@ static int grid_for(Kern kern, int threads, size_t smem, int warps_per_block, in
 static int launch_rel(RelStepParams& p, int variant, cudaStream_t stream) {
   static const int dbg = getenv("MKE_DEBUG_SKIP") ? atoi(getenv("MKE_DEBUG_SKIP")) : 0;
   p.dbg = dbg;
+  // debug: MKE_TRACE=<file> dumps per-warp milestone timestamps of launch number MKE_TRACE_AT
+  static const char* trace_path = getenv("MKE_TRACE");
+  static const int trace_at = getenv("MKE_TRACE_AT") ? atoi(getenv("MKE_TRACE_AT")) : 50;
+  static int trace_calls = 0;
+  p.trace = nullptr;
+  unsigned long long* trace_buf = nullptr;
+  const size_t trace_words = (size_t)1 << 20;
+  if (trace_path != nullptr && trace_calls++ == trace_at) {
+    if (cudaMalloc(&trace_buf, trace_words * 8) == cudaSuccess) {
+      cudaMemsetAsync(trace_buf, 0, trace_words * 8, stream);
+      p.trace = trace_buf;
+    }
+  }
+  struct TraceDump {
+    unsigned long long* buf; size_t words; const char* path; cudaStream_t stream;
+    ~TraceDump() {
+      if (!buf) return;
+      cudaStreamSynchronize(stream);
+      unsigned long long* host = (unsigned long long*)malloc(words * 8);
+      cudaMemcpy(host, buf, words * 8, cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(path, "wb")) { fwrite(host, 8, words, f); fclose(f); }
+      free(host);
+      cudaFree(buf);
+    }
+  } trace_dump{trace_buf, trace_words, trace_path, stream};
   const int n = p.len1 + p.len2;
   if (n <= 0) return 0;
   const int nv = (p.nchunk + 31) / 32;
@@ -522,6 +549,8 @@ static void fill_tables(RelStepParams& p, const mke_table_t* ent, const mke_tabl
   p.ent_touched = ent->touched;
   p.rel_var = rel->var;
   p.rel_grad = rel->grad;
+  p.rel_rep = rel->grad_replicas > 1 ? rel->grad_replicas : 1;
+  p.rel_rep_floats = (size_t)rel->rows * (size_t)rel->stride;
   p.rel_touched = rel->touched;
   p.stride = ent->stride;
   p.nchunk = (ent->dim + 3) / 4;
@@ -573,23 +602,25 @@ extern "C" int mke_rel_step_sampled(const mke_table_t* ent, const mke_table_t* r
   return launch_rel(p, variant, (cudaStream_t)stream);
 }
 
-extern "C" int mke_rel_step_structured(const mke_table_t* ent, const mke_table_t* rel,
-                                       const int32_t* pos, int32_t n, int32_t K,
-                                       const int32_t* neg_ent, const uint32_t* neg_side,
-                                       const float* w_or_null, float pos_scale, double* loss_accum,
-                                       int32_t variant, mke_stream_t stream) {
+extern "C" int mke_rel_step_structured2(const mke_table_t* ent, const mke_table_t* rel,
+                                        const int32_t* pos1, int32_t len1, const int32_t* pos2,
+                                        int32_t len2, int32_t K, const int32_t* neg_ent,
+                                        const uint32_t* neg_side, const float* w_or_null,
+                                        float pos_scale, double* loss_accum, int32_t variant,
+                                        mke_stream_t stream) {
   if (int rc = validate_tables(ent, rel)) return rc;
   MKE_CHECK_ARG(K >= 0 && K <= MKE_MAX_NEG, "K=%d outside [0,%d]", K, MKE_MAX_NEG);
-  MKE_CHECK_ARG(n >= 0, "negative batch length");
-  MKE_CHECK_ARG(n == 0 || pos, "pos is null");
-  MKE_CHECK_ARG(K == 0 || n == 0 || (neg_ent && neg_side), "neg_ent/neg_side are null");
+  MKE_CHECK_ARG(len1 >= 0 && len2 >= 0, "negative batch length");
+  MKE_CHECK_ARG((uint64_t)len1 + (uint64_t)len2 < (1ull << 31), "batch too large");
+  MKE_CHECK_ARG((len1 == 0 || pos1) && (len2 == 0 || pos2), "pos is null");
+  MKE_CHECK_ARG(K == 0 || len1 + len2 == 0 || (neg_ent && neg_side), "neg_ent/neg_side are null");
   MKE_CHECK_ARG(loss_accum, "loss_accum is null");
   RelStepParams p{};
   fill_tables(p, ent, rel);
-  p.pos1 = pos;
-  p.len1 = n;
-  p.pos2 = nullptr;
-  p.len2 = 0;
+  p.pos1 = pos1;
+  p.len1 = len1;
+  p.pos2 = pos2;
+  p.len2 = len2;
   p.K = K;
   p.sampled = 0;
   p.neg_ent = neg_ent;
@@ -599,4 +630,13 @@ extern "C" int mke_rel_step_structured(const mke_table_t* ent, const mke_table_t
   p.loss = loss_accum;
   p.neg_out = nullptr;
   return launch_rel(p, variant, (cudaStream_t)stream);
+}
+
+extern "C" int mke_rel_step_structured(const mke_table_t* ent, const mke_table_t* rel,
+                                       const int32_t* pos, int32_t n, int32_t K,
+                                       const int32_t* neg_ent, const uint32_t* neg_side,
+                                       const float* w_or_null, float pos_scale, double* loss_accum,
+                                       int32_t variant, mke_stream_t stream) {
+  return mke_rel_step_structured2(ent, rel, pos, n, nullptr, 0, K, neg_ent, neg_side, w_or_null,
+                                  pos_scale, loss_accum, variant, stream);
 }

@@ -10,6 +10,8 @@ struct RelStepParams {
   uint8_t* ent_touched;
   const float* rel_var;
   float* rel_grad;
+  int rel_rep;              // gradient replicas of the relation table (>= 1)
+  size_t rel_rep_floats;    // floats per replica = rows * stride
   uint8_t* rel_touched;
   int stride;    // floats per row (both tables)
   int nchunk;    // float4 pieces per row that carry data = ceil(dim/4)
@@ -29,6 +31,7 @@ struct RelStepParams {
   float pos_scale;
   double* loss;
   int32_t* neg_out;
+  unsigned long long* trace;  // debug: per-warp milestone clocks (MKE_TRACE), else NULL
   int dbg;  // timing experiments only (MKE_DEBUG_SKIP): bit0 no rel RED, bit1 no touched, bit2 no loss atomic, bit3 no ent RED, bit4 no hash probe
 };
 
@@ -41,6 +44,11 @@ __device__ __forceinline__ void softplus_sigmoid(float x, float& sp, float& sg) 
   const float one_p = 1.0f + ex;
   sp = __logf(one_p);
   sg = __fdividef(ex, one_p);
+}
+
+// this thread block's copy of the relation gradient table (mke_table_t.grad_replicas)
+__device__ __forceinline__ float* rel_grad_replica(const RelStepParams& p) {
+  return p.rel_grad + (size_t)(blockIdx.x % (unsigned)p.rel_rep) * p.rel_rep_floats;
 }
 
 // quarter-warp kernel (mke_rel_q8.cu); returns 1 when the stride has no instantiation

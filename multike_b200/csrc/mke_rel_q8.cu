@@ -16,12 +16,10 @@
 // and accumulates d loss / d row into the gradient tables with red.global.add (vectorised).
 #include <cstdlib>
 #include "mke_rel.cuh"
+#include "mke_sampler.cuh"
 
 namespace mke {
 
-constexpr int kQPerWarp = 4;     // positives per warp
-constexpr int kPickStride = 33;  // MKE_MAX_NEG + 1: the four quarters of a warp hit distinct banks
-constexpr uint32_t kFull = 0xffffffffu;
 
 __device__ __forceinline__ float qsum(float v) {
   v += __shfl_xor_sync(kFull, v, 4);
@@ -92,105 +90,6 @@ __device__ __forceinline__ float sumsq(const float (&x)[FPL]) {
 #pragma unroll
   for (int k = 0; k < FPL; ++k) s = fmaf(x[k], x[k], s);
   return s;
-}
-
-// ---- sampler, quarter layout --------------------------------------------------------------
-struct KgView {  // mke_kg_sampler_t selected per quarter (kg1 / kg2), held in registers
-  const int32_t* list;
-  const int32_t* neighbours;
-  mke_tripleset_t set;
-  int32_t base, n, n_nb;
-  __device__ __forceinline__ CandPool pool(int32_t anchor) const {
-    CandPool c;
-    if (neighbours != nullptr) {
-      const int32_t* row = neighbours + (size_t)anchor * (size_t)n_nb;
-      if (__ldg(row) >= 0) {
-        c.list = row;
-        c.base = 0;
-        c.n = (uint32_t)n_nb;
-        return c;
-      }
-    }
-    c.list = list;
-    c.base = base;
-    c.n = (uint32_t)n;
-    return c;
-  }
-};
-__device__ __forceinline__ KgView kg_view(const RelStepParams& p, bool first) {
-  KgView k;
-  k.list = first ? p.kg1.entity_list : p.kg2.entity_list;
-  k.neighbours = first ? p.kg1.neighbours : p.kg2.neighbours;
-  k.set.slots = first ? p.kg1.set.slots : p.kg2.set.slots;
-  k.set.capacity = first ? p.kg1.set.capacity : p.kg2.set.capacity;
-  k.base = first ? p.kg1.entity_base : p.kg2.entity_base;
-  k.n = first ? p.kg1.n_entities : p.kg2.n_entities;
-  k.n_nb = first ? p.kg1.n_neighbours : p.kg2.n_neighbours;
-  return k;
-}
-__device__ __forceinline__ uint32_t low_ones(int k) { return (k >= 32) ? kFull : ((1u << k) - 1u); }
-
-// generate_neg_triples_fast (base/batch.py:86-116) for ONE positive, executed by the 8 lanes of a
-// quarter with exactly the sequential semantics that oracle/device_sampler.py restates:
-//   per round (<= MKE_MAX_TRY): one head/tail coin; candidates c = 0, 1, 2, ... are drawn from the
-//   pool of the replaced entity and accepted unless they repeat an entity already accepted in this
-//   round (random.sample = without replacement) until `remaining` are accepted; accepted
-//   candidates that are known triples are dropped (not in the last round); stop at K.
-// Draws are counter based, so the 8 lanes evaluate candidates c_base + sub of a chunk at once
-// and ranks inside the chunk reproduce the sequential order.  All synchronisation is scoped to
-// the quarter (qmask): the four quarters of a warp may be in different rounds.
-// Writes pick[0..K) and returns the side mask (bit j: negative j replaces the head).
-__device__ __forceinline__ uint32_t sample_negs_quarter(const KgView& kg, int32_t h, int32_t r,
-                                                        int32_t t, int K, uint64_t skey, uint32_t i,
-                                                        int lane, volatile int32_t* pick) {
-  const int sub = lane & 7;
-  const int qshift = lane & 24;
-  const uint32_t qmask = 0xffu << qshift;
-  const uint32_t below = (1u << sub) - 1u;  // lower lanes of my quarter, after shifting to bit 0
-  int n_acc = 0, remaining = K;
-  uint32_t side_mask = 0;
-  for (uint32_t tr = 0; tr < MKE_MAX_TRY; ++tr) {
-    const bool head_side = (draw64(skey, i, tr, kSideDraw) >> 63) != 0;
-    const CandPool pool = kg.pool(head_side ? h : t);
-    // ---- draw: accept the first `remaining` candidates that do not repeat an accepted one ----
-    int np = 0;
-    for (uint32_t c_base = 0; np < remaining; c_base += 8) {
-      const uint32_t c = c_base + (uint32_t)sub;
-      const int32_t e = pool.at(draw_index(draw64(skey, i, tr, c), pool.n));
-      bool dup = false;
-      for (int k = 0; k < np; ++k) dup |= (pick[n_acc + k] == e);
-      const uint32_t same = (__match_any_sync(qmask, e) >> qshift) & 0xffu;
-      dup |= (same & below) != 0u;
-      dup = dup && (c + 1u < kSideDraw);
-      const uint32_t fresh = (__ballot_sync(qmask, !dup) >> qshift) & 0xffu;
-      const int rank = __popc(fresh & below);
-      __syncwarp(qmask);  // all lanes have compared against pick[] before it grows
-      if (!dup && np + rank < remaining) pick[n_acc + np + rank] = e;
-      __syncwarp(qmask);
-      np = min(remaining, np + __popc(fresh));
-    }
-    // ---- filter: drop known triples (the last round is accepted as is, batch.py:103-105) ------
-    int kept = np;
-    if (tr != MKE_MAX_TRY - 1) {
-      kept = 0;
-      for (int k0 = 0; k0 < np; k0 += 8) {
-        const int k = k0 + sub;
-        const int32_t e = pick[n_acc + (k < np ? k : 0)];
-        const uint64_t key = head_side ? triple_key(e, r, t) : triple_key(h, r, e);
-        const bool keep = (k < np) && !tripleset_contains(kg.set, key);
-        const uint32_t kb = (__ballot_sync(qmask, keep) >> qshift) & 0xffu;
-        // the ballot doubles as the barrier between reading pick[] above and compacting it
-        if (keep) pick[n_acc + kept + __popc(kb & below)] = e;
-        __syncwarp(qmask);
-        kept += __popc(kb);
-      }
-    }
-    if (head_side && kept > 0) side_mask |= low_ones(kept) << n_acc;
-    n_acc += kept;
-    if (n_acc >= K) break;
-    remaining = K - n_acc;
-  }
-  return side_mask;
 }
 
 // A negative whose side differs from the side of negative 0 of its positive (only possible when
@@ -308,11 +207,74 @@ struct Stage {
   }
 };
 
-template <int FPL, int THREADS, int MINB>
+// ---- gradient rows back to HBM ---------------------------------------------------------------
+// BULK == false: red.global.add.v4/v2.f32 from registers (24 LSU lane-operations per 80-float row).
+// BULK == true : the quarter writes the row into its 320-byte shared buffer and its leader lane
+//                hands it to the TMA engine (cp.reduce.async.bulk .add.f32, SASS UBLKRED): the
+//                element-wise add happens at L2 like RED, but off the LSU, which the gather side
+//                (LDGSTS/LDS) keeps busy.  profiles/ has the A/B measurement.
+template <int FPL, bool BULK>
+struct RowScatter {
+  uint32_t buf;  // shared-space address of this quarter's row buffer
+  uint32_t qmask;
+  int sub;
+  // called quarter-uniformly (all 8 lanes of the quarter or none)
+  __device__ __forceinline__ void add(float* __restrict__ grad_row, const float (&x)[FPL], float s) const {
+    if constexpr (!BULK) {
+      red_row<FPL>(grad_row, sub, x, s);
+    } else {
+      constexpr int NV4 = FPL / 4, REM = FPL % 4;
+      // the engine must have finished READING the previous row out of the buffer
+      if (sub == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp(qmask);
+#pragma unroll
+      for (int c = 0; c < NV4; ++c)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (c * 8 + sub) * 16),
+                     "f"(x[4 * c] * s), "f"(x[4 * c + 1] * s), "f"(x[4 * c + 2] * s), "f"(x[4 * c + 3] * s)
+                     : "memory");
+      const uint32_t tail = buf + NV4 * 128 + REM * 4 * sub;
+      if constexpr (REM == 2)
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(tail), "f"(x[4 * NV4] * s), "f"(x[4 * NV4 + 1] * s)
+                     : "memory");
+      if constexpr (REM == 1 || REM == 3) {
+#pragma unroll
+        for (int k = 0; k < REM; ++k)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(tail + 4 * k), "f"(x[4 * NV4 + k] * s) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
+      __syncwarp(qmask);
+      if (sub == 0) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(grad_row),
+                     "r"(buf), "n"(FPL * 32)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  __device__ __forceinline__ void drain() const {
+    if constexpr (BULK) {
+      if (sub == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
+#define MKE_TRACE(slot)                                                                        \
+  do {                                                                                         \
+    if (p.trace != nullptr && lane == 0)                                                       \
+      p.trace[(size_t)(blockIdx.x * WARPS + wib) * 32 + (slot)] = gtimer();                   \
+  } while (0)
+
+template <int FPL, int THREADS, int MINB, bool BULK>
 __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelStepParams p) {
   constexpr int WARPS = THREADS / 32;
   constexpr int stride = FPL * 8;
-  __shared__ __align__(16) unsigned char s_stage[WARPS][Stage<FPL>::kBytes];
+  __shared__ __align__(128) unsigned char s_stage[WARPS][Stage<FPL>::kBytes];
+  __shared__ __align__(128) float s_out[BULK ? WARPS : 1][kQPerWarp][BULK ? stride : 1];
   __shared__ int32_t s_pick_all[WARPS][kQPerWarp][kPickStride];
   __shared__ float s_loss[WARPS];
   const int lane = threadIdx.x & 31;
@@ -323,10 +285,16 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
   Stage<FPL> stg;
   stg.base = (uint32_t)__cvta_generic_to_shared(&s_stage[wib][0]);
   stg.lane = lane;
+  RowScatter<FPL, BULK> out;
+  out.buf = (uint32_t)__cvta_generic_to_shared(&s_out[BULK ? wib : 0][q][0]);
+  out.qmask = 0xffu << (lane & 24);
+  out.sub = sub;
   const int n = p.len1 + p.len2;
   const int K = p.K;
   const int per_pass = gridDim.x * WARPS * kQPerWarp;
+  float* const rel_grad = rel_grad_replica(p);
   float loss_local = 0.f;
+  MKE_TRACE(0);
 
   for (int i0 = (blockIdx.x * WARPS + wib) * kQPerWarp; i0 < n; i0 += per_pass) {
     const int i = i0 + q;
@@ -342,6 +310,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
     {
       uint32_t side = 0u;
       const bool active = valid;
+      if (h + r + t == -3) MKE_TRACE(15);  // (forces the id loads to have landed)
+      MKE_TRACE(1);
       // the three rows of the positive travel to shared memory while the sampler probes
       stg.issue(0, p.ent_var + (size_t)h * stride, sub);
       stg.issue(1, p.rel_var + (size_t)r * stride, sub);
@@ -355,7 +325,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
             kg.neighbours = nullptr;
             kg.set.slots = nullptr;
           }
-          side = sample_negs_quarter(kg, h, r, t, K, p.skey, (uint32_t)i, lane, pick);
+          side = sample_negs_quarter(kg, h, r, t, K, p.skey, (uint32_t)i, lane, pick,
+                                     p.trace ? p.trace + (size_t)(blockIdx.x * WARPS + wib) * 32 : nullptr);
           if (!valid) {
             side = 0u;
             for (int c = sub; c < K; c += 8) pick[c] = 0;
@@ -376,6 +347,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
           }
         }
       }
+      MKE_TRACE(2);
       // ---- positive term -----------------------------------------------------------------
       const bool side0 = (side & 1u) != 0u;  // side of negative 0: true = head replaced
       const float sgn = side0 ? 1.f : -1.f;
@@ -389,6 +361,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         stg.read(2, xt);
         float sh = sumsq<FPL>(xh), sr = sumsq<FPL>(xr), st = sumsq<FPL>(xt);
         qsum3(sh, sr, st);
+        if (sh == -1.f) MKE_TRACE(15);
+        MKE_TRACE(3);
         // the slots are free again (their contents fed the sums above): first negatives go out
 #pragma unroll
         for (int j = 0; j < kSlots; ++j) {
@@ -422,11 +396,13 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
 #pragma unroll
         for (int k = 0; k < FPL; ++k) acc[k] *= cp;  // d loss / d pd; the K-loop adds the negatives
         // the endpoint that no same-side negative shares gets its positive-term gradient now
-        if (active && !(p.dbg & 8)) red_row<FPL>(p.ent_grad + (size_t)(side0 ? h : t) * stride, sub, acc, sgn);
+        if (active && !(p.dbg & 8)) out.add(p.ent_grad + (size_t)(side0 ? h : t) * stride, acc, sgn);
       }
+      MKE_TRACE(4);
       // ---- negatives: rows j+1, j+2 are in flight while row j is scored ------------------------
       int slot = 0;
       for (int j = 0; j < K; ++j) {
+        if (j < 8) MKE_TRACE(5 + j);
         float x[FPL];
         cp_async_wait<kSlots - 1>();
         stg.read(slot, x);
@@ -462,35 +438,39 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
           x[k] = fmaf(x[k], sie, base[k]);  // neg_distance (losses.py:6)
           acc[k] = fmaf(cn, x[k], acc[k]);
         }
-        if (on && !(p.dbg & 8)) red_row<FPL>(p.ent_grad + (size_t)e * stride, sub, x, cn * sgn);
+        if (on && !(p.dbg & 8)) out.add(p.ent_grad + (size_t)e * stride, x, cn * sgn);
       }
       cp_async_wait<0>();
+      MKE_TRACE(13);
       // ---- r gets every same-side term, the shared endpoint likewise -----------------------
       if (active) {
-        if (!(p.dbg & 1)) red_row<FPL>(p.rel_grad + (size_t)r * stride, sub, acc, 1.f);
-        if (!(p.dbg & 8)) red_row<FPL>(p.ent_grad + (size_t)(side0 ? t : h) * stride, sub, acc, -sgn);
+        if (!(p.dbg & 1)) out.add(rel_grad + (size_t)r * stride, acc, 1.f);
+        if (!(p.dbg & 8)) out.add(p.ent_grad + (size_t)(side0 ? t : h) * stride, acc, -sgn);
         if (!(p.dbg & 2)) {
-        for (int c = sub; c < K; c += 8) p.ent_touched[pick[c]] = 1;
+        for (int c = sub; c < K; c += 8) mark_touched(p.ent_touched, pick[c]);
         if (sub == 0) {
-          p.ent_touched[h] = 1;
-          p.ent_touched[t] = 1;
-          p.rel_touched[r] = 1;
+          mark_touched(p.ent_touched, h);
+          mark_touched(p.ent_touched, t);
+          mark_touched(p.rel_touched, r);
         }
         }
       }
+      MKE_TRACE(19);
       // ---- negatives on the other side than negative 0 (rare), once base/acc are dead ------
       const bool mixed = active && side != 0u && side != low_ones(K);
       if (__any_sync(kFull, mixed)) {
         for (int j = 1; j < K; ++j) {
           const bool odd = active && ((((side >> j) & 1u) != 0u) != side0);
           if (__any_sync(kFull, odd))
-            loss_local += odd_negative<FPL>(p.ent_var, p.rel_var, p.ent_grad, p.rel_grad, p.ent_norm,
+            loss_local += odd_negative<FPL>(p.ent_var, p.rel_var, p.ent_grad, rel_grad, p.ent_norm,
                                             p.rel_norm, h, r, t, pick[j], !side0, odd, sub);
         }
       }
       __syncwarp();  // pick[] is rewritten by the next positive
+      MKE_TRACE(14);
     }
   }
+  out.drain();
   // ---- loss: quarter leaders -> warp -> block -> one fp64 atomic ------------------------------
   float v = (sub == 0) ? loss_local : 0.f;
   v = warp_sum(v);
@@ -504,9 +484,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
   }
 }
 
-template <int FPL, int THREADS, int MINB>
+template <int FPL, int THREADS, int MINB, bool BULK>
 static int launch_q8(const RelStepParams& p, cudaStream_t stream) {
-  auto kern = rel_fused_q8_kernel<FPL, THREADS, MINB>;
+  auto kern = rel_fused_q8_kernel<FPL, THREADS, MINB, BULK>;
   constexpr int per_block = (THREADS / 32) * kQPerWarp;
   const int n = p.len1 + p.len2;
   static int per_sm_cached = 0;
@@ -527,15 +507,18 @@ static int launch_q8(const RelStepParams& p, cudaStream_t stream) {
 int launch_rel_q8(const RelStepParams& p, cudaStream_t stream) {
   static const int cfg = getenv("MKE_Q8_CFG") ? atoi(getenv("MKE_Q8_CFG")) : 0;  // tuning knob
   switch (p.stride) {
-    case 32: return launch_q8<4, 64, 16>(p, stream);
-    case 64: return launch_q8<8, 64, 16>(p, stream);
+    case 32: return launch_q8<4, 64, 16, false>(p, stream);
+    case 64: return launch_q8<8, 64, 16, false>(p, stream);
     case 80:
-      if (cfg == 1) return launch_q8<10, 64, 16>(p, stream);
-      if (cfg == 2) return launch_q8<10, 64, 20>(p, stream);
-      if (cfg == 3) return launch_q8<10, 128, 8>(p, stream);
-      return launch_q8<10, 64, 18>(p, stream);
-    case 104: return launch_q8<13, 64, 12>(p, stream);
-    case 128: return launch_q8<16, 64, 12>(p, stream);
+      if (cfg == 1) return launch_q8<10, 64, 18, false>(p, stream);
+      if (cfg == 2) return launch_q8<10, 64, 16, true>(p, stream);
+      if (cfg == 3) return launch_q8<10, 64, 9, false>(p, stream);
+      if (cfg == 4) return launch_q8<10, 64, 12, false>(p, stream);
+      if (cfg == 5) return launch_q8<10, 128, 6, false>(p, stream);
+      if (cfg == 6) return launch_q8<10, 256, 2, false>(p, stream);
+      return launch_q8<10, 64, 18, true>(p, stream);
+    case 104: return launch_q8<13, 64, 12, false>(p, stream);
+    case 128: return launch_q8<16, 64, 12, false>(p, stream);
     default: return 1;
   }
 }

@@ -2,7 +2,7 @@
 // Replaces the Python set membership test and generate_neg_triples_fast of
 // base/batch.py:86-116 (all_triples_set = kg.local_relation_triples_set, which aliases
 // relation_triples_set and therefore also holds the swapped sup triples: base/kg.py:59,134).
-#include "mke_common.cuh"
+#include "mke_sampler.cuh"
 
 namespace mke {
 
@@ -33,33 +33,78 @@ __global__ void tripleset_contains_kernel(mke_tripleset_t set, const int32_t* __
   }
 }
 
-constexpr int kSampThreads = 256;
+constexpr int kSampThreads = 128;
 constexpr int kSampWarps = kSampThreads / 32;
 
+// One positive per quarter warp, the same sampler (and therefore the same draws) as the fused
+// relation kernel.  Output either as (h,r,t) rows, positive-major (what base/batch.py:116
+// returns), or in the structured form mke_rel_step_structured consumes.
 __global__ void __launch_bounds__(kSampThreads)
     sample_kernel(const int32_t* __restrict__ pos1, int len1, mke_kg_sampler_t kg1,
                   const int32_t* __restrict__ pos2, int len2, mke_kg_sampler_t kg2, int K,
-                  uint64_t skey, int32_t* __restrict__ neg_out) {
-  __shared__ int32_t s_pick_all[kSampWarps][32];
+                  uint64_t skey, int32_t* __restrict__ neg_out, int32_t* __restrict__ neg_ent,
+                  uint32_t* __restrict__ neg_side) {
+  __shared__ int32_t s_pick_all[kSampWarps][kQPerWarp][kPickStride];
   const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  const int q = lane >> 3;
   const int wib = threadIdx.x >> 5;
+  volatile int32_t* pick = s_pick_all[wib][q];
   const int n = len1 + len2;
-  for (int i = blockIdx.x * kSampWarps + wib; i < n; i += gridDim.x * kSampWarps) {
-    const bool first = i < len1;
-    const int32_t* row = first ? pos1 + 3 * (size_t)i : pos2 + 3 * (size_t)(i - len1);
-    const int32_t h = __ldg(row), r = __ldg(row + 1), t = __ldg(row + 2);
-    int32_t e;
-    uint32_t side;
-    sample_negs_warp(first ? kg1 : kg2, h, r, t, K, skey, (uint32_t)i, lane, s_pick_all[wib], e,
-                     side);
-    if (lane < K) {
-      const bool hs = (side >> lane) & 1u;
-      int32_t* o = neg_out + ((size_t)i * K + lane) * 3;
-      o[0] = hs ? e : h;
-      o[1] = r;
-      o[2] = hs ? t : e;
+  const int per_pass = gridDim.x * kSampWarps * kQPerWarp;
+  for (int i0 = (blockIdx.x * kSampWarps + wib) * kQPerWarp; i0 < n; i0 += per_pass) {
+    const int i = i0 + q;
+    if (i < n) {  // quarters are independent: the sampler only synchronises inside a quarter
+      const bool first = i < len1;
+      const int32_t* row = first ? pos1 + 3 * (size_t)i : pos2 + 3 * (size_t)(i - len1);
+      const int32_t h = __ldg(row), r = __ldg(row + 1), t = __ldg(row + 2);
+      const KgView kg = kg_view(kg1, kg2, first);
+      const uint32_t side = sample_negs_quarter(kg, h, r, t, K, skey, (uint32_t)i, lane, pick);
+      for (int c = sub; c < K; c += 8) {
+        const int32_t e = pick[c];
+        if (neg_ent != nullptr) neg_ent[(size_t)i * K + c] = e;
+        if (neg_out != nullptr) {
+          const bool hs = (side >> c) & 1u;
+          int32_t* o = neg_out + ((size_t)i * K + c) * 3;
+          o[0] = hs ? e : h;
+          o[1] = r;
+          o[2] = hs ? t : e;
+        }
+      }
+      if (neg_side != nullptr && sub == 0) neg_side[i] = side;
+      __syncwarp(0xffu << (lane & 24));  // pick[] is rewritten by this quarter's next positive
     }
   }
+}
+
+static int launch_sample(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                         const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2, int32_t K,
+                         uint64_t seed, uint64_t step, int32_t* neg_out, int32_t* neg_ent,
+                         uint32_t* neg_side, cudaStream_t stream) {
+  MKE_CHECK_ARG(K >= 1 && K <= MKE_MAX_NEG, "K=%d outside [1,%d]", K, MKE_MAX_NEG);
+  MKE_CHECK_ARG(len1 >= 0 && len2 >= 0, "negative batch length");
+  MKE_CHECK_ARG(len1 == 0 || (pos1 && kg1), "kg1 slice needs positives and a sampler");
+  MKE_CHECK_ARG(len2 == 0 || (pos2 && kg2), "kg2 slice needs positives and a sampler");
+  const int n = len1 + len2;
+  if (n == 0) return 0;
+  mke_kg_sampler_t a{}, b{};
+  if (kg1) a = *kg1;
+  if (kg2) b = *kg2;
+  for (const mke_kg_sampler_t* kg : {len1 ? kg1 : nullptr, len2 ? kg2 : nullptr}) {
+    if (!kg) continue;
+    MKE_CHECK_ARG(kg->n_entities >= K, "KG has fewer entities (%d) than K=%d", kg->n_entities, K);
+    MKE_CHECK_ARG(!kg->neighbours || kg->n_neighbours >= K, "n_neighbours < K");
+    MKE_CHECK_ARG(!kg->set.slots || (kg->set.capacity >= 8 && (kg->set.capacity & (kg->set.capacity - 1)) == 0),
+                  "triple-set capacity must be a power of two >= 8");
+  }
+  constexpr int per_block = kSampWarps * kQPerWarp;
+  int blocks = (n + per_block - 1) / per_block;
+  const int full = sm_count() * 16;
+  if (blocks > full) blocks = full;
+  sample_kernel<<<blocks, kSampThreads, 0, stream>>>(pos1, len1, a, pos2, len2, b, K, stream_key(seed, step),
+                                                     neg_out, neg_ent, neg_side);
+  MKE_CHECK_LAUNCH("sample_kernel");
+  return 0;
 }
 
 static int check_set(const mke_tripleset_t* set) {
@@ -102,26 +147,16 @@ extern "C" int mke_sample_uniform(const int32_t* pos1, int32_t len1, const mke_k
                                   const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
                                   int32_t K, uint64_t seed, uint64_t step, int32_t* neg_out,
                                   mke_stream_t stream) {
-  MKE_CHECK_ARG(K >= 1 && K <= MKE_MAX_NEG, "K=%d outside [1,%d]", K, MKE_MAX_NEG);
-  MKE_CHECK_ARG(len1 >= 0 && len2 >= 0, "negative batch length");
-  MKE_CHECK_ARG(len1 == 0 || (pos1 && kg1), "kg1 slice needs positives and a sampler");
-  MKE_CHECK_ARG(len2 == 0 || (pos2 && kg2), "kg2 slice needs positives and a sampler");
-  const int n = len1 + len2;
-  if (n == 0) return 0;
-  MKE_CHECK_ARG(neg_out, "neg_out is null");
-  mke_kg_sampler_t a{}, b{};
-  if (kg1) a = *kg1;
-  if (kg2) b = *kg2;
-  for (const mke_kg_sampler_t* kg : {len1 ? kg1 : nullptr, len2 ? kg2 : nullptr}) {
-    if (!kg) continue;
-    MKE_CHECK_ARG(kg->n_entities >= K, "KG has fewer entities (%d) than K=%d", kg->n_entities, K);
-    MKE_CHECK_ARG(!kg->neighbours || kg->n_neighbours >= K, "n_neighbours < K");
-  }
-  int blocks = (n + kSampWarps - 1) / kSampWarps;
-  const int full = sm_count() * 8;
-  if (blocks > full) blocks = full;
-  sample_kernel<<<blocks, kSampThreads, 0, (cudaStream_t)stream>>>(pos1, len1, a, pos2, len2, b, K,
-                                                                  stream_key(seed, step), neg_out);
-  MKE_CHECK_LAUNCH("sample_kernel");
-  return 0;
+  MKE_CHECK_ARG(neg_out || len1 + len2 == 0, "neg_out is null");
+  return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, neg_out, nullptr, nullptr,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int mke_sample_structured(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                                     const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                                     int32_t K, uint64_t seed, uint64_t step, int32_t* neg_ent,
+                                     uint32_t* neg_side, mke_stream_t stream) {
+  MKE_CHECK_ARG((neg_ent && neg_side) || len1 + len2 == 0, "neg_ent/neg_side are null");
+  return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, nullptr, neg_ent, neg_side,
+                       (cudaStream_t)stream);
 }

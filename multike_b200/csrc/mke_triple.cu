@@ -10,6 +10,8 @@ namespace mke {
 struct TripleParams {
   const float *vh, *vm, *vt;
   float *gh, *gm, *gt;
+  int rh, rm, rt;           // gradient replicas per table (>= 1)
+  size_t fh_, fm_, ft_;     // floats per replica
   uint8_t *fh, *fm, *ft;
   int sh, sm, st;  // strides
   int nh, nm, nt;  // normalised flags
@@ -34,6 +36,9 @@ __global__ void __launch_bounds__(kTripleThreads) triple_fwd_bwd_kernel(const Tr
   const int gwarp = blockIdx.x * kTripleWarps + wib;
   const int nwarps = gridDim.x * kTripleWarps;
   float loss_local = 0.f;
+  float* const gh = p.gh ? p.gh + (size_t)(blockIdx.x % (unsigned)p.rh) * p.fh_ : nullptr;
+  float* const gm = p.gm ? p.gm + (size_t)(blockIdx.x % (unsigned)p.rm) * p.fm_ : nullptr;
+  float* const gt = p.gt ? p.gt + (size_t)(blockIdx.x % (unsigned)p.rt) * p.ft_ : nullptr;
   for (int i = gwarp; i < p.n; i += nwarps) {
     const int32_t h = __ldg(p.ih + i), m = __ldg(p.im + i), t = __ldg(p.it + i);
     const float* ph = p.vh + (size_t)h * p.sh;
@@ -77,15 +82,15 @@ __global__ void __launch_bounds__(kTripleThreads) triple_fwd_bwd_kernel(const Tr
       const int cidx = lane + 32 * v;
       if (cidx < p.nchunk) {
         const float4 g = f4_scale(d[v], c);
-        if (p.gh) red_add_f4(p.gh + (size_t)h * p.sh + 4 * cidx, g);
-        if (p.gm) red_add_f4(p.gm + (size_t)m * p.sm + 4 * cidx, g);
-        if (p.gt) red_add_f4(p.gt + (size_t)t * p.st + 4 * cidx, f4_scale(g, -1.f));
+        if (gh) red_add_f4(gh + (size_t)h * p.sh + 4 * cidx, g);
+        if (gm) red_add_f4(gm + (size_t)m * p.sm + 4 * cidx, g);
+        if (gt) red_add_f4(gt + (size_t)t * p.st + 4 * cidx, f4_scale(g, -1.f));
       }
     }
     if (lane == 0) {
-      if (p.fh) p.fh[h] = 1;
-      if (p.fm) p.fm[m] = 1;
-      if (p.ft) p.ft[t] = 1;
+      mark_touched(p.fh, h);
+      mark_touched(p.fm, m);
+      mark_touched(p.ft, t);
     }
   }
   __shared__ float s_loss[kTripleWarps];
@@ -130,8 +135,6 @@ extern "C" int mke_triple_fwd_bwd(const mke_table_t* head, const mke_table_t* mi
   for (const mke_table_t* tb : {head, mid, tail}) {
     MKE_CHECK_ARG(tb->stride % 4 == 0 && tb->dim <= tb->stride, "bad stride %d for dim %d",
                   tb->stride, tb->dim);
-    MKE_CHECK_ARG(tb->grad == nullptr || tb->touched != nullptr,
-                  "trainable table needs a touched array");
   }
   MKE_CHECK_ARG(n >= 0, "negative n");
   if (n == 0) return 0;
@@ -139,6 +142,12 @@ extern "C" int mke_triple_fwd_bwd(const mke_table_t* head, const mke_table_t* mi
   TripleParams p{};
   p.vh = head->var; p.vm = mid->var; p.vt = tail->var;
   p.gh = head->grad; p.gm = mid->grad; p.gt = tail->grad;
+  p.rh = head->grad_replicas > 1 ? head->grad_replicas : 1;
+  p.rm = mid->grad_replicas > 1 ? mid->grad_replicas : 1;
+  p.rt = tail->grad_replicas > 1 ? tail->grad_replicas : 1;
+  p.fh_ = (size_t)head->rows * head->stride;
+  p.fm_ = (size_t)mid->rows * mid->stride;
+  p.ft_ = (size_t)tail->rows * tail->stride;
   p.fh = head->grad ? head->touched : nullptr;
   p.fm = mid->grad ? mid->touched : nullptr;
   p.ft = tail->grad ? tail->touched : nullptr;

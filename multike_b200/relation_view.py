@@ -37,7 +37,7 @@ class RelationView:
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size=5000, neg_num=10,
                  lr=0.001, seed=0, device="cuda", variant=0, ent_init=None, rel_init=None,
-                 filter1=None, filter2=None, generator=None):
+                 filter1=None, filter2=None, generator=None, pipelined=True):
         _cabi.load()
         self.device = torch.device(device)
         self.dim, self.batch_size, self.K, self.lr = int(dim), int(batch_size), int(neg_num), float(lr)
@@ -47,7 +47,7 @@ class RelationView:
         if rel_init is None:
             rel_init = T.xavier_truncated_normal(n_rel, dim, generator)
         # base/initializers.py:22-26 with is_l2_norm=True (MultiKE_model.py:92-95)
-        self.ent = T.EmbeddingTable(n_ent, dim, True, device, init=ent_init, name="rv_ent_embeds")
+        self.ent = T.EmbeddingTable(n_ent, dim, True, device, init=ent_init, name="rv_ent_embeds", grad_replicas=1)
         self.rel = T.EmbeddingTable(n_rel, dim, True, device, init=rel_init, name="rel_embeds")
         t1 = np.ascontiguousarray(triples1, dtype=np.int32).reshape(-1, 3)
         t2 = np.ascontiguousarray(triples2, dtype=np.int32).reshape(-1, 3)
@@ -64,6 +64,15 @@ class RelationView:
         self.global_step = 0
         self._lib = _cabi.load()
         self.phase1_events = None  # optional list of (start, end) CUDA events around phase 1
+        # Negatives of step s+1 are drawn on a second stream while step s trains: sampling reads
+        # no embedding table (only triples, the filter set and the counter-based RNG), so it has
+        # no dependence on the Adagrad update in flight.  Two buffers, used alternately.
+        self.pipelined = bool(pipelined) and self.K > 0
+        if self.pipelined:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._neg = [(torch.empty(self.batch_size, self.K, dtype=torch.int32, device=self.device),
+                          torch.empty(self.batch_size, dtype=torch.int32, device=self.device)) for _ in range(2)]
+            self._ready = {}  # global step -> (buffer index, event) of negatives already drawn
 
     # -- bookkeeping of the reference drivers -------------------------------------------------
     @property
@@ -95,17 +104,60 @@ class RelationView:
             ev[1].record()
             self.phase1_events.append(ev)
 
-    def _phase2(self):
-        self.ent.apply_adagrad("relation", self.lr)
-        self.rel.apply_adagrad("relation", self.lr)
+    def _sample_into(self, buf, pos1, len1, pos2, len2, step, stream):
+        ne, ns = self._neg[buf]
+        _cabi.check(self._lib.mke_sample_structured(
+            pos1, len1, self.kg1.c, pos2, len2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), step,
+            ne.data_ptr(), ns.data_ptr(), stream))
 
-    def step_resident(self, step_in_epoch):
-        """One training step on positives already in HBM; returns the number of positives."""
+    def _phase1_presampled(self, buf, pos1, len1, pos2, len2):
+        ne, ns = self._neg[buf]
+        ev = None
+        if self.phase1_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _cabi.check(self._lib.mke_rel_step_structured2(
+            self.ent.c, self.rel.c, pos1, len1, pos2, len2, self.K, ne.data_ptr(), ns.data_ptr(), None, 1.0,
+            self.loss_acc.data_ptr(), self.variant, _cabi.current_stream()))
+        if ev is not None:
+            ev[1].record()
+            self.phase1_events.append(ev)
+
+    def _slice_ptrs(self, step_in_epoch):
         (a1, b1), (a2, b2) = self.step_slices(step_in_epoch)
-        len1, len2 = b1 - a1, b2 - a2
+        return self.triples1.data_ptr() + 12 * a1, b1 - a1, self.triples2.data_ptr() + 12 * a2, b2 - a2
+
+    def _phase2(self):
+        T.apply_adagrad_pair(self.ent, self.ent.adagrad_slot("relation"), self.lr,
+                             self.rel, self.rel.adagrad_slot("relation"), self.lr)
+
+    def step_resident(self, step_in_epoch, next_step_in_epoch=None):
+        """One training step on positives already in HBM; returns the number of positives.
+        `next_step_in_epoch` (pipelined mode): the step whose negatives are drawn meanwhile."""
+        p1, len1, p2, len2 = self._slice_ptrs(step_in_epoch)
         if len1 + len2 == 0:
             return 0
-        self._phase1(self.triples1.data_ptr() + 12 * a1, len1, self.triples2.data_ptr() + 12 * a2, len2)
+        if not self.pipelined:
+            self._phase1(p1, len1, p2, len2)
+        else:
+            main = torch.cuda.current_stream()
+            ready = self._ready.pop(self.global_step, None)
+            if ready is None:  # nothing drawn ahead (first step, epoch boundary): draw in line
+                buf = self.global_step & 1
+                self._sample_into(buf, p1, len1, p2, len2, self.global_step, main.cuda_stream)
+            else:
+                buf, ev = ready
+                main.wait_event(ev)
+            self._phase1_presampled(buf, p1, len1, p2, len2)
+            if next_step_in_epoch is not None:
+                q1, m1, q2, m2 = self._slice_ptrs(next_step_in_epoch)
+                if m1 + m2 > 0:
+                    # starts when phase 1 of this step has finished, i.e. overlaps the (HBM-bound)
+                    # apply kernel; the other buffer was last read by the previous step's phase 1
+                    fence = main.record_event()
+                    self._side.wait_event(fence)
+                    self._sample_into(buf ^ 1, q1, m1, q2, m2, self.global_step + 1, self._side.cuda_stream)
+                    self._ready[self.global_step + 1] = (buf ^ 1, self._side.record_event())
         self._phase2()
         self.global_step += 1
         return len1 + len2
@@ -137,8 +189,9 @@ class RelationView:
         loss stays on the device until the end of the epoch.  Returns (avg loss, #positives)."""
         self.loss_acc.zero_()
         trained = 0
-        for s in range(self.triple_steps):
-            trained += self.step_resident(s)
+        steps = self.triple_steps
+        for s in range(steps):
+            trained += self.step_resident(s, s + 1 if s + 1 < steps else None)
         loss = float(self.loss_acc.item())
         if shuffle:  # MultiKE_model.py:314-315 random.shuffle of both lists
             self.triples1 = self.triples1[torch.randperm(self.n1, device=self.device, generator=generator)]

@@ -10,6 +10,7 @@ MultiKE_model.py:28-31).
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -35,7 +36,12 @@ def xavier_truncated_normal(rows, dim, generator=None, device="cpu"):
 class EmbeddingTable:
     """One tf.get_variable (+ optional l2_normalize(var, 1) view) of MultiKE_model.py:86-107."""
 
-    def __init__(self, rows, dim, normalised, device="cuda", init=None, trainable=True, name=""):
+    FLAGS_MIN_ROWS = 8192  # smaller tables are swept whole by phase 2 (mke_table_t.touched = NULL)
+    # ... and get this many gradient copies (mke_table_t.grad_replicas)
+    SMALL_TABLE_REPLICAS = int(os.environ.get("MKE_SMALL_REPLICAS", "7"))
+
+    def __init__(self, rows, dim, normalised, device="cuda", init=None, trainable=True, name="", flags=None,
+                 grad_replicas=None):
         self.rows, self.dim, self.normalised, self.name = int(rows), int(dim), bool(normalised), name
         self.stride = padded_stride(dim)
         self.device = torch.device(device)
@@ -45,9 +51,16 @@ class EmbeddingTable:
             assert tuple(src.shape) == (self.rows, self.dim), (src.shape, self.rows, self.dim)
             self.var[:, : self.dim] = src.to(self.device, torch.float32)
         self.trainable = bool(trainable)
+        self.grad_replicas = 1
         if self.trainable:
-            self.grad = torch.zeros_like(self.var)
-            self.touched = torch.zeros(self.rows, dtype=torch.uint8, device=self.device)
+            if grad_replicas is None:
+                grad_replicas = self.SMALL_TABLE_REPLICAS if self.rows < self.FLAGS_MIN_ROWS else 1
+            self.grad_replicas = max(1, int(grad_replicas))
+            shape = (self.rows, self.stride) if self.grad_replicas == 1 else (self.grad_replicas, self.rows, self.stride)
+            self.grad = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            if flags is None:
+                flags = self.rows >= self.FLAGS_MIN_ROWS
+            self.touched = torch.zeros(self.rows, dtype=torch.uint8, device=self.device) if flags else None
         else:
             self.grad = None
             self.touched = None
@@ -56,12 +69,17 @@ class EmbeddingTable:
             var=self.var.data_ptr(),
             grad=_cabi.ptr(self.grad),
             touched=_cabi.ptr(self.touched),
-            rows=self.rows, stride=self.stride, dim=self.dim, normalised=int(self.normalised))
+            rows=self.rows, stride=self.stride, dim=self.dim, normalised=int(self.normalised),
+            grad_replicas=self.grad_replicas)
 
     # -- C view ---------------------------------------------------------------------------
     @property
     def c(self):
         return ctypes.byref(self._c)
+
+    def grad_sum(self):
+        """[rows, stride] gradient accumulated so far (replicas summed)."""
+        return self.grad if self.grad_replicas == 1 else self.grad.sum(0)
 
     # -- optimizer slots --------------------------------------------------------------------
     def adagrad_slot(self, slot):
@@ -231,6 +249,13 @@ def apply_adagrad(table, acc, lr):
     _cabi.check(lib.mke_rows_apply_adagrad(table.c, acc.data_ptr(), float(lr), _cabi.current_stream()))
 
 
+def apply_adagrad_pair(table_a, acc_a, lr_a, table_b, acc_b, lr_b):
+    """mke_rows_apply_adagrad_pair: phase 2 of two tables in one launch."""
+    lib = _cabi.load()
+    _cabi.check(lib.mke_rows_apply_adagrad_pair(table_a.c, acc_a.data_ptr(), float(lr_a), table_b.c, acc_b.data_ptr(),
+                                                float(lr_b), _cabi.current_stream()))
+
+
 def sample_uniform(pos1, kg1, pos2, kg2, K, seed, step, device="cuda"):
     """mke_sample_uniform: the negatives the fused kernel would draw, as [(len1+len2)*K, 3]."""
     lib = _cabi.load()
@@ -243,3 +268,18 @@ def sample_uniform(pos1, kg1, pos2, kg2, K, seed, step, device="cuda"):
                                        int(K), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
                                        out.data_ptr(), _cabi.current_stream()))
     return out
+
+
+def sample_structured(pos1, kg1, pos2, kg2, K, seed, step, device="cuda"):
+    """mke_sample_structured: (neg_ent [n,K] int32, neg_side [n] int32 bit masks)."""
+    lib = _cabi.load()
+    pos1, pos2 = _i32(pos1, device), _i32(pos2, device)
+    len1 = 0 if pos1 is None else pos1.numel() // 3
+    len2 = 0 if pos2 is None else pos2.numel() // 3
+    ne = torch.empty(len1 + len2, K, dtype=torch.int32, device=device)
+    ns = torch.empty(len1 + len2, dtype=torch.int32, device=device)
+    _cabi.check(lib.mke_sample_structured(_cabi.ptr(pos1), len1, kg1.c if kg1 is not None else None,
+                                          _cabi.ptr(pos2), len2, kg2.c if kg2 is not None else None,
+                                          int(K), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
+                                          ne.data_ptr(), ns.data_ptr(), _cabi.current_stream()))
+    return ne, ns

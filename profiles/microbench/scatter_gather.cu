@@ -56,6 +56,48 @@ __global__ void __launch_bounds__(256) k_reg(const float* __restrict__ tab, floa
   if (MODE == 0 && acc == 123.456f) *sink = acc;
 }
 
+// mode 7: gather a row with LDG.128 and RED.v4 it into the gradient table (both directions in one
+//         kernel, the access pattern of the fused relation kernel without its arithmetic)
+// mode 8: the same in the quarter-warp layout (8 lanes x (v4,v4,v2) per row, 4 rows per warp op)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_both(const float* __restrict__ tab, float* __restrict__ grad,
+                                              const int32_t* __restrict__ idx, int npos, int stride) {
+  const int lane = threadIdx.x & 31;
+  if (MODE == 7) {
+    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    for (int i = gw; i < npos; i += nw) {
+      int32_t my = (lane < ROWS_PER_POS) ? __ldg(idx + (size_t)i * ROWS_PER_POS + lane) : 0;
+      float4 v[ROWS_PER_POS];
+#pragma unroll
+      for (int j = 0; j < ROWS_PER_POS; ++j) {
+        const int32_t r = __shfl_sync(0xffffffffu, my, j);
+        v[j] = (lane < NCHUNK) ? __ldg(reinterpret_cast<const float4*>(tab + (size_t)r * stride) + lane) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS_PER_POS; ++j) {
+        const int32_t r = __shfl_sync(0xffffffffu, my, j);
+        if (lane < NCHUNK) red_v4(grad + (size_t)r * stride + 4 * lane, v[j]);
+      }
+    }
+  } else {
+    const int sub = lane & 7, q = lane >> 3;
+    const int gq = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + q, nq = gridDim.x * 32;
+    for (int i = gq; i < npos; i += nq) {
+      for (int j = 0; j < ROWS_PER_POS; ++j) {
+        const int32_t r = __ldg(idx + (size_t)i * ROWS_PER_POS + j);
+        const float* row = tab + (size_t)r * stride;
+        float* g = grad + (size_t)r * stride;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row) + sub);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(row) + 8 + sub);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(row + 64) + sub);
+        red_v4(g + 4 * sub, a);
+        red_v4(g + 32 + 4 * sub, b);
+        red_v2(g + 64 + 2 * sub, c.x, c.y);
+      }
+    }
+  }
+}
+
 // mode 5: bulk gather (cp.async.bulk g2s, 304 B / row, one mbarrier per warp, 13 rows in flight)
 // mode 6: bulk reduce-add s2g (cp.reduce.async.bulk .add.f32, 304 B / row)
 template <int MODE, int WARPS>
@@ -140,7 +182,7 @@ int main(int argc, char** argv) {
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     CK(cudaGetLastError());
-    printf("%-34s %8.2f us/launch  %8.1f GB/s (300 B/row)\n", name, 1e3 * ms / iters, bytes / (ms / iters * 1e-3) / 1e9);
+    printf("%-34s %8.2f us/launch  %8.1f GB/s (300 B/row, one direction)\n", name, 1e3 * ms / iters, bytes / (ms / iters * 1e-3) / 1e9);
   };
   for (int bps : {4, 8}) {
     const int grid = 148 * bps;
@@ -150,6 +192,12 @@ int main(int argc, char** argv) {
     timeit("scatter RED.v2.f32", [&](int q) { k_reg<4><<<grid, 256>>>(tab, grad, idx + (size_t)q * npos * ROWS_PER_POS, npos, stride, sink); });
     timeit("scatter RED.f32 (scalar)", [&](int q) { k_reg<2><<<grid, 256>>>(tab, grad, idx + (size_t)q * npos * ROWS_PER_POS, npos, stride, sink); });
     timeit("scatter ST.v4 (no add)", [&](int q) { k_reg<3><<<grid, 256>>>(tab, grad, idx + (size_t)q * npos * ROWS_PER_POS, npos, stride, sink); });
+  }
+  for (int bps : {4, 8}) {
+    const int grid = 148 * bps;
+    printf("-- gather + scatter in one kernel, grid = 148 x %d blocks of 256 thr\n", bps);
+    timeit("LDG.128 + RED.v4, warp/positive", [&](int q) { k_both<7><<<grid, 256>>>(tab, grad, idx + (size_t)q * npos * ROWS_PER_POS, npos, stride); });
+    timeit("LDG + RED, quarter/positive", [&](int q) { k_both<8><<<grid, 256>>>(tab, grad, idx + (size_t)q * npos * ROWS_PER_POS, npos, stride); });
   }
   {
     constexpr int W = 8;

@@ -8,17 +8,21 @@ from multike_b200 import tables as T
 DEV = "cuda"
 
 
-def make_tables(ent0, rel0, ent_norm=True, rel_norm=True):
+def make_tables(ent0, rel0, ent_norm=True, rel_norm=True, flags=(True, True), rel_replicas=None):
+    """flags: per table, True = touched-byte map, False = mke_table_t.touched NULL (phase 2 sweeps
+    every row), None = the product default (by table size)."""
     ent0 = np.asarray(ent0, dtype=np.float32)
     rel0 = np.asarray(rel0, dtype=np.float32)
-    ent = T.EmbeddingTable(ent0.shape[0], ent0.shape[1], ent_norm, DEV, init=ent0, name="ent")
-    rel = T.EmbeddingTable(rel0.shape[0], rel0.shape[1], rel_norm, DEV, init=rel0, name="rel")
+    ent = T.EmbeddingTable(ent0.shape[0], ent0.shape[1], ent_norm, DEV, init=ent0, name="ent", flags=flags[0],
+                           grad_replicas=1)
+    rel = T.EmbeddingTable(rel0.shape[0], rel0.shape[1], rel_norm, DEV, init=rel0, name="rel", flags=flags[1],
+                           grad_replicas=rel_replicas)
     return ent, rel
 
 
 def grad_np(table):
     torch.cuda.synchronize()
-    return table.grad[:, : table.dim].double().cpu().numpy()
+    return table.grad_sum()[:, : table.dim].double().cpu().numpy()
 
 
 def pad_is_zero(table):
@@ -27,7 +31,7 @@ def pad_is_zero(table):
         return True
     ok = float(table.var[:, table.dim:].abs().max()) == 0.0
     if table.grad is not None:
-        ok = ok and float(table.grad[:, table.dim:].abs().max()) == 0.0
+        ok = ok and float(table.grad[..., table.dim:].abs().max()) == 0.0
     return ok
 
 

@@ -74,6 +74,35 @@ def test_fused_structured_step_matches_golden(G, golden, fname, variant):
     np.testing.assert_allclose(rel.raw(), g["rel3"], rtol=0, atol=3 * ROW_ATOL)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("flags,rel_replicas", [((False, False), 1), ((True, False), 5), ((None, None), None),
+                                                ((True, True), 3)])
+def test_step_without_touched_flags(G, golden, variant, flags, rel_replicas):
+    """mke_table_t.touched == NULL: phase 1 writes no flags, phase 2 sweeps every row (a zero
+    gradient row is an Adagrad no-op); mke_table_t.grad_replicas > 1: phase 1 spreads the
+    relation-row reductions over R copies, phase 2 sums and re-zeroes them -- same result as the
+    flagged single-copy path."""
+    U, T = G
+    g = golden("relation_step_d75.npz")
+    K, lr = int(g["K"]), float(g["lr"])
+    ent, rel = U.make_tables(g["ent0"], g["rel0"], flags=flags, rel_replicas=rel_replicas)
+    acc = T.new_loss_accumulator()
+    for step in range(3):
+        acc.zero_()
+        T.rel_step_structured(ent, rel, g["pos"], g["neg_ent"], g["neg_side"], K, acc, variant=variant)
+        if step == 0:
+            assert U.loss_value(acc) == pytest.approx(float(g["loss"]), rel=LOSS_RTOL)
+        T.apply_adagrad_pair(ent, ent.adagrad_slot("r"), lr, rel, rel.adagrad_slot("r"), lr)
+    keep = np.ones(ent.rows, bool)
+    keep[5] = False
+    np.testing.assert_allclose(ent.raw()[keep], g["ent3"][keep], rtol=0, atol=3 * ROW_ATOL)
+    np.testing.assert_allclose(rel.raw(), g["rel3"], rtol=0, atol=3 * ROW_ATOL)
+    assert float(ent.grad.abs().max()) == 0.0 and float(rel.grad.abs().max()) == 0.0
+    # untouched rows keep their bits even when swept
+    untouched = np.abs(g["view_grad_ent"]).sum(1) == 0
+    assert untouched.any() and np.array_equal(ent.raw()[untouched], g["ent0"][untouched].astype(np.float32))
+
+
 @pytest.mark.parametrize("fname", ["relation_step_d75.npz", "relation_step_d128.npz"])
 def test_generic_triple_op_matches_golden(G, golden, fname):
     """mke_triple_fwd_bwd in the reference's own 6-index form (losses.py:4-12): two calls."""
@@ -228,6 +257,37 @@ def test_fused_sampled_step_equals_sampler_plus_structured(G, golden, variant):
     np.testing.assert_allclose(U.grad_np(rel), gR.numpy(), rtol=GRAD_RTOL, atol=GRAD_ATOL)
 
 
+def test_structured_sampler_and_pipelined_driver(G, golden):
+    """mke_sample_structured draws what mke_sample_uniform / the fused kernel draw, and the
+    two-stream driver (negatives of step s+1 drawn while step s trains) ends in the same tables
+    as the fused single-kernel step."""
+    U, T = G
+    from multike_b200.relation_view import RelationView
+    n_ent, t1, t2, all1, all2, nb1, nb2 = _golden_kgs(golden)
+    K = 10
+    dk1 = T.KGSampler(entity_base=0, n_entities=n_ent, triple_set=T.TripleSet(all1))
+    dk2 = T.KGSampler(entity_base=n_ent, n_entities=n_ent, triple_set=T.TripleSet(all2))
+    p1, p2 = t1[:77], t2[:50]
+    ne, ns = T.sample_structured(p1, dk1, p2, dk2, K, 3, 8)
+    trip = T.sample_uniform(p1, dk1, p2, dk2, K, 3, 8).cpu().numpy()
+    pos = np.concatenate([p1, p2])
+    back = orv.structured_to_negatives(pos, ne.cpu().numpy(), ns.cpu().numpy().view(np.uint32), K)
+    assert np.array_equal(back, trip)
+    gen = torch.Generator().manual_seed(11)
+    ent0 = T.xavier_truncated_normal(2 * n_ent, 75, gen)
+    rel0 = T.xavier_truncated_normal(5, 75, gen)
+    out = []
+    for pipelined in (False, True):
+        rv = RelationView(2 * n_ent, 5, 75, t1, t2, n_ent, batch_size=200, neg_num=K, lr=0.001, seed=5,
+                          ent_init=ent0, rel_init=rel0, filter1=all1, filter2=all2, pipelined=pipelined)
+        losses = [rv.train_epoch(shuffle=False)[0] for _ in range(2)]
+        torch.cuda.synchronize()
+        out.append((losses, rv.ent.var.clone(), rv.rel.var.clone()))
+    assert out[0][0] == pytest.approx(out[1][0], rel=1e-6)
+    torch.testing.assert_close(out[0][1], out[1][1], rtol=0, atol=ROW_ATOL)
+    torch.testing.assert_close(out[0][2], out[1][2], rtol=0, atol=ROW_ATOL)
+
+
 def test_tripleset_membership(G, golden):
     U, T = G
     n_ent, t1, t2, all1, all2, _, _ = _golden_kgs(golden)
@@ -359,11 +419,11 @@ def test_full_size_linearity_and_variant_agreement(G, full):
         ent, rel = U.make_tables(ent0.numpy(), rel0.numpy())
         acc = T.new_loss_accumulator()
         T.rel_step_sampled(ent, rel, p1, kg1, p2, kg2, K, 7, 3, acc, variant=variant)
-        outs.append((U.loss_value(acc), ent.grad.clone(), rel.grad.clone()))
+        outs.append((U.loss_value(acc), ent.grad_sum().clone(), rel.grad_sum().clone()))
         if variant == 0:
             T.rel_step_sampled(ent, rel, p1, kg1, p2, kg2, K, 7, 3, acc, variant=variant)
             assert U.loss_value(acc) == pytest.approx(2 * outs[0][0], rel=1e-6)
-            torch.testing.assert_close(ent.grad, 2 * outs[0][1], rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(ent.grad_sum(), 2 * outs[0][1], rtol=1e-4, atol=1e-5)
     for other in outs[1:]:
         assert outs[0][0] == pytest.approx(other[0], rel=1e-6)
         torch.testing.assert_close(outs[0][1], other[1], rtol=1e-4, atol=2e-5)
@@ -376,13 +436,47 @@ def test_full_size_linearity_and_variant_agreement(G, full):
     T.triple_fwd_bwd(ent, rel, ent, pos[:, 0], pos[:, 1], pos[:, 2], acc)
     T.triple_fwd_bwd(ent, rel, ent, neg[:, 0], neg[:, 1], neg[:, 2], acc, negative=True)
     assert U.loss_value(acc) == pytest.approx(outs[0][0], rel=1e-6)
-    torch.testing.assert_close(ent.grad, outs[0][1], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(ent.grad_sum(), outs[0][1], rtol=1e-4, atol=2e-5)
+
+
+def test_pair_apply_equals_two_single_applies(G, golden):
+    """mke_rows_apply_adagrad_pair (one launch for the entity + relation table) == two calls of
+    mke_rows_apply_adagrad, bit for bit; different learning rates per table are honoured."""
+    U, T = G
+    g = golden("relation_step_d75.npz")
+    K = int(g["K"])
+    res = []
+    for pair in (False, True):
+        ent, rel = U.make_tables(g["ent0"], g["rel0"])
+        acc = T.new_loss_accumulator()
+        T.rel_step_structured(ent, rel, g["pos"], g["neg_ent"], g["neg_side"], K, acc)
+        if pair:
+            T.apply_adagrad_pair(ent, ent.adagrad_slot("s"), 0.001, rel, rel.adagrad_slot("s"), 0.004)
+        else:
+            ent.apply_adagrad("s", 0.001)
+            rel.apply_adagrad("s", 0.004)
+        torch.cuda.synchronize()
+        res.append((ent.var.clone(), rel.var.clone(), ent.adagrad_slot("s").clone(), rel.adagrad_slot("s").clone()))
+        assert float(ent.grad.abs().max()) == 0 and int(ent.touched.max()) == 0
+        assert float(rel.grad.abs().max()) == 0 and int(rel.touched.max()) == 0
+    # phase 1 uses float atomics (order varies run to run) -> compare within the row tolerance
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=ROW_ATOL)
+    # mismatched strides fall back to two launches
+    ent, _ = U.make_tables(g["ent0"], g["rel0"])
+    other = T.EmbeddingTable(9, 32, False, "cuda", init=np.ones((9, 32), np.float32), flags=True)
+    other.grad[3, :32] = 2.0
+    other.touched[3] = 1
+    T.apply_adagrad_pair(ent, ent.adagrad_slot("s"), 0.001, other, other.adagrad_slot("s"), 0.5)
+    want = 1.0 - 0.5 * 2.0 / np.sqrt(0.1 + 4.0)
+    np.testing.assert_allclose(other.raw()[3], want, rtol=1e-6)
+    assert np.array_equal(other.raw()[2], np.ones(32, np.float32))
 
 
 def test_bad_arguments_on_device(G):
     U, T = G
     from multike_b200 import _cabi
-    ent = T.EmbeddingTable(10, 75, True, "cuda")
+    ent = T.EmbeddingTable(10, 75, True, "cuda", grad_replicas=1)
     rel = T.EmbeddingTable(3, 64, True, "cuda")
     with pytest.raises(_cabi.MkeError):
         T.rel_step_structured(ent, rel, np.zeros((1, 3), np.int32), None, None, 0, T.new_loss_accumulator())
