@@ -44,6 +44,16 @@ def bytes_per_positive(dim, K):
     return 2 * (3 + K) * dim * 4 + 12
 
 
+def ncu_traffic(workload, kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            k = json.load(fh)[workload][kernel]
+        return k["dram_read_bytes"] + k["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -267,7 +277,10 @@ def main():
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "rel_fused (phase 1)",
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload, "rel_fused_q8_kernel") if args.variant == 0 else None,
+                         "traffic_note": "dram bytes per launch, ncu --set full (cold L2), profiles/r1_traffic.json",
+                         "algorithmic_bytes": alg_bytes, "kernel": "rel_fused_q8_kernel (phase 1)",
                          "peak_source": peak_kind, "launch_ms": p1_ms,
                          "bytes_per_positive": bytes_per_positive(dim, K)},
         }

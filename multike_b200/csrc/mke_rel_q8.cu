@@ -506,19 +506,21 @@ static int launch_q8(const RelStepParams& p, cudaStream_t stream) {
 // strides with a quarter-warp instantiation: 32 (dim<=32), 64, 80 (dim 75), 104 (dim 100), 128
 int launch_rel_q8(const RelStepParams& p, cudaStream_t stream) {
   static const int cfg = getenv("MKE_Q8_CFG") ? atoi(getenv("MKE_Q8_CFG")) : 0;  // tuning knob
+  // <floats per lane, threads per block, min blocks per SM, TMA bulk-reduce scatter>.  The defaults
+  // come from the sweep in profiles/r1_phase1_tuning.md: fewer, fatter blocks (more registers, no
+  // spills) beat maximum occupancy because the kernel is bound by row traffic, not by issue.
   switch (p.stride) {
-    case 32: return launch_q8<4, 64, 16, false>(p, stream);
-    case 64: return launch_q8<8, 64, 16, false>(p, stream);
+    case 32: return launch_q8<4, 128, 8, false>(p, stream);
+    case 64: return launch_q8<8, 128, 6, false>(p, stream);
     case 80:
       if (cfg == 1) return launch_q8<10, 64, 18, false>(p, stream);
       if (cfg == 2) return launch_q8<10, 64, 16, true>(p, stream);
       if (cfg == 3) return launch_q8<10, 64, 9, false>(p, stream);
-      if (cfg == 4) return launch_q8<10, 64, 12, false>(p, stream);
-      if (cfg == 5) return launch_q8<10, 128, 6, false>(p, stream);
+      if (cfg == 4) return launch_q8<10, 128, 6, true>(p, stream);
       if (cfg == 6) return launch_q8<10, 256, 2, false>(p, stream);
-      return launch_q8<10, 64, 18, true>(p, stream);
-    case 104: return launch_q8<13, 64, 12, false>(p, stream);
-    case 128: return launch_q8<16, 64, 12, false>(p, stream);
+      return launch_q8<10, 128, 6, false>(p, stream);
+    case 104: return launch_q8<13, 128, 5, false>(p, stream);
+    case 128: return launch_q8<16, 128, 4, false>(p, stream);
     default: return 1;
   }
 }
