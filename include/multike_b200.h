@@ -184,6 +184,64 @@ int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
                                 const mke_table_t* b, float* acc_b, float lr_b, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Step / epoch driver.
+ * ------------------------------------------------------------------------------------------ */
+
+/*
+ * Everything train_relation_view_1epo (MultiKE_model.py:291-317) touches, as the kernels see it.
+ * The triple lists of both KGs live either in HBM (triples1/2) or in pinned HOST memory
+ * (host_triples1/2, then stage1/2 must hold two device staging buffers of b1*3 / b2*3 int32 each,
+ * b1 = int(n1/(n1+n2)*batch_size), b2 = batch_size - b1, base/batch.py:36-37).
+ */
+typedef struct mke_rel_view {
+  const mke_table_t* ent;          /* rv_ent_embeds (MultiKE_model.py:92)                       */
+  const mke_table_t* rel;          /* rel_embeds    (MultiKE_model.py:93)                       */
+  float*  ent_acc;                 /* Adagrad slot of this graph for ent ([rows,stride])        */
+  float*  rel_acc;
+  float   lr;                      /* args.learning_rate                                        */
+  const int32_t* triples1;         /* device [n1,3] or NULL                                     */
+  const int32_t* triples2;
+  const int32_t* host_triples1;    /* pinned host [n1,3] or NULL                                */
+  const int32_t* host_triples2;
+  int32_t* stage1[2];              /* device staging for host-fed batches                       */
+  int32_t* stage2[2];
+  int32_t n1, n2;
+  const mke_kg_sampler_t* kg1;
+  const mke_kg_sampler_t* kg2;
+  int32_t batch_size;              /* args.batch_size                                           */
+  int32_t K;                       /* args.neg_triple_num                                       */
+  uint64_t seed;
+  int32_t*  neg_ent[2];            /* [batch_size*K] x2, or NULL => negatives drawn inside phase 1 */
+  uint32_t* neg_side[2];           /* [batch_size]   x2                                         */
+  double* step_loss;               /* device [>= n_steps]: loss of step s is ADDED to step_loss[s] */
+  double* host_step_loss;          /* pinned host [>= n_steps] or NULL: step_loss[s] is copied
+                                      here (async, 8 bytes) after every step                    */
+  int32_t variant;
+} mke_rel_view_t;
+
+/*
+ * n_steps consecutive training steps (batch -> negatives -> phase 1 -> phase 2), starting at step
+ * `first_step` of an epoch and wrapping to step 0 after the last step of the epoch
+ * (ceil((n1+n2)/batch_size) steps, MultiKE_CSL.py:40) -- the inner loop of
+ * MultiKE_model.py:302-313 without any host round trip.  Step s uses RNG coordinate
+ * first_global_step + s.  With neg_ent != NULL the negatives (and, for host-fed batches, the
+ * H2D copy) of step s+1 run on `side` while step s trains on `main`; both streams are joined
+ * again before return (the call is capturable into a CUDA graph).  positives_out (host, may be
+ * NULL) receives the number of positives trained (trained_samples_num, MultiKE_model.py:311).
+ */
+int mke_rel_train_steps(const mke_rel_view_t* view, int32_t first_step, int32_t n_steps,
+                        uint64_t first_global_step, int64_t* positives_out,
+                        mke_stream_t main, mke_stream_t side);
+
+/*
+ * Measurement aid (the only entry points that synchronise): after mke_timing_enable(n) the driver
+ * brackets each of its next n phase-1 launches with CUDA events on `main`; mke_timing_read waits
+ * for them, returns the summed elapsed time and the number of launches, and re-arms.
+ */
+int mke_timing_enable(int32_t max_launches);
+int mke_timing_read(double* total_ms, int32_t* launches);
+
+/* ------------------------------------------------------------------------------------------
  * Sampler pieces (base/batch.py:86-116, attr_batch.py:13-25) usable on their own.
  * ------------------------------------------------------------------------------------------ */
 

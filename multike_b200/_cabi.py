@@ -45,6 +45,24 @@ class MkeKgSampler(_c.Structure):
     ]
 
 
+class MkeRelView(_c.Structure):
+    _fields_ = [
+        ("ent", _c.POINTER(MkeTable)), ("rel", _c.POINTER(MkeTable)),
+        ("ent_acc", _c.c_void_p), ("rel_acc", _c.c_void_p),
+        ("lr", _c.c_float),
+        ("triples1", _c.c_void_p), ("triples2", _c.c_void_p),
+        ("host_triples1", _c.c_void_p), ("host_triples2", _c.c_void_p),
+        ("stage1", _c.c_void_p * 2), ("stage2", _c.c_void_p * 2),
+        ("n1", _c.c_int32), ("n2", _c.c_int32),
+        ("kg1", _c.POINTER(MkeKgSampler)), ("kg2", _c.POINTER(MkeKgSampler)),
+        ("batch_size", _c.c_int32), ("K", _c.c_int32),
+        ("seed", _c.c_uint64),
+        ("neg_ent", _c.c_void_p * 2), ("neg_side", _c.c_void_p * 2),
+        ("step_loss", _c.c_void_p), ("host_step_loss", _c.c_void_p),
+        ("variant", _c.c_int32),
+    ]
+
+
 _PT = _c.POINTER(MkeTable)
 _PS = _c.POINTER(MkeTripleSet)
 _PK = _c.POINTER(MkeKgSampler)
@@ -60,6 +78,9 @@ SIGNATURES = {
                                     _f32, _vp, _vp, _i32, _vp]),
     "mke_rel_step_structured": (_i32, [_PT, _PT, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rel_step_structured2": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
+    "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
+    "mke_timing_enable": (_i32, [_i32]),
+    "mke_timing_read": (_i32, [_c.POINTER(_c.c_double), _c.POINTER(_i32)]),
     "mke_rows_apply_adagrad": (_i32, [_PT, _vp, _f32, _vp]),
     "mke_rows_apply_adagrad_pair": (_i32, [_PT, _vp, _f32, _PT, _vp, _f32, _vp]),
     "mke_tripleset_build": (_i32, [_PS, _vp, _i32, _vp]),

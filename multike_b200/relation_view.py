@@ -2,14 +2,16 @@
 ``MultiKE.train_relation_view_1epo`` (MultiKE_model.py:291-317).
 
 What the reference does per step and where it lives here:
-  base/batch.py:33-54    batch = kg1 slice ++ kg2 slice, sizes by KG share   -> step_slices()
-  base/batch.py:86-116   K negatives per positive, filtered                  -> on device, inside
-                                                                               mke_rel_step_sampled
-  MultiKE_model.py:123-131 + losses.py:4-12  gathers, score, loss, backward  -> mke_rel_step_sampled
-  MultiKE_model.py:15-31  Adagrad (own accumulators per graph)               -> mke_rows_apply_adagrad
-  MultiKE_model.py:311-315 loss bookkeeping, list shuffle                    -> epoch drivers below
+  base/batch.py:33-54    batch = kg1 slice ++ kg2 slice, sizes by KG share   -> mke_rel_train_steps
+  base/batch.py:86-116   K negatives per positive, filtered                  -> mke_sample_structured
+                                                                               (or inside phase 1)
+  MultiKE_model.py:123-131 + losses.py:4-12  gathers, score, loss, backward  -> phase 1 kernel
+  MultiKE_model.py:15-31  Adagrad (own accumulators per graph)               -> phase 2 kernel
+  MultiKE_model.py:302-315 step loop, loss bookkeeping, list shuffle         -> mke_rel_train_steps,
+                                                                               train_epoch below
 No TF, no CPU fallback: every call goes through the C-ABI library (multike_b200/_cabi.py).
 """
+import ctypes
 import math
 
 import numpy as np
@@ -32,13 +34,15 @@ def clipped_slice(n, bs, step):
 
 
 class RelationView:
-    """rv_ent_embeds + rel_embeds, their Adagrad slots, the device-resident triple lists of both
-    KGs and the negative samplers."""
+    """rv_ent_embeds + rel_embeds, their Adagrad slots, the triple lists of both KGs (device
+    resident, and optionally a pinned host copy for host-fed steps) and the negative samplers."""
+
+    SLOT = "relation"  # one Adagrad accumulator set per loss graph (MultiKE_model.py:28-31)
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size=5000, neg_num=10,
                  lr=0.001, seed=0, device="cuda", variant=0, ent_init=None, rel_init=None,
                  filter1=None, filter2=None, generator=None, pipelined=True):
-        _cabi.load()
+        self._lib = _cabi.load()
         self.device = torch.device(device)
         self.dim, self.batch_size, self.K, self.lr = int(dim), int(batch_size), int(neg_num), float(lr)
         self.seed, self.variant = int(seed), int(variant)
@@ -60,19 +64,39 @@ class RelationView:
         self.kg1 = T.KGSampler(entity_base=0, n_entities=ent_split, triple_set=self.set1, device=device)
         self.kg2 = T.KGSampler(entity_base=ent_split, n_entities=n_ent - ent_split, triple_set=self.set2,
                                device=device)
-        self.loss_acc = T.new_loss_accumulator(device)
         self.global_step = 0
-        self._lib = _cabi.load()
-        self.phase1_events = None  # optional list of (start, end) CUDA events around phase 1
         # Negatives of step s+1 are drawn on a second stream while step s trains: sampling reads
         # no embedding table (only triples, the filter set and the counter-based RNG), so it has
         # no dependence on the Adagrad update in flight.  Two buffers, used alternately.
         self.pipelined = bool(pipelined) and self.K > 0
+        self._side = torch.cuda.Stream(device=self.device)
+        self._neg = None
         if self.pipelined:
-            self._side = torch.cuda.Stream(device=self.device)
-            self._neg = [(torch.empty(self.batch_size, self.K, dtype=torch.int32, device=self.device),
+            self._neg = [(torch.empty(self.batch_size * self.K, dtype=torch.int32, device=self.device),
                           torch.empty(self.batch_size, dtype=torch.int32, device=self.device)) for _ in range(2)]
-            self._ready = {}  # global step -> (buffer index, event) of negatives already drawn
+        self._step_loss = torch.zeros(max(self.triple_steps, 1), dtype=torch.float64, device=self.device)
+        self._last_steps = 0
+        self._host_loss = None
+        self._host_triples = None
+        self._stage = None
+        self._view = _cabi.MkeRelView()
+        self._fill_view()
+
+    # -- C view -----------------------------------------------------------------------------
+    def _fill_view(self):
+        v = self._view
+        v.ent, v.rel = ctypes.pointer(self.ent._c), ctypes.pointer(self.rel._c)
+        v.ent_acc = self.ent.adagrad_slot(self.SLOT).data_ptr()
+        v.rel_acc = self.rel.adagrad_slot(self.SLOT).data_ptr()
+        v.lr = self.lr
+        v.triples1, v.triples2 = self.triples1.data_ptr(), self.triples2.data_ptr()
+        v.n1, v.n2 = self.n1, self.n2
+        v.kg1, v.kg2 = ctypes.pointer(self.kg1._c), ctypes.pointer(self.kg2._c)
+        v.batch_size, v.K, v.seed, v.variant = self.batch_size, self.K, self.seed & (2 ** 64 - 1), self.variant
+        for k in range(2):
+            v.neg_ent[k] = self._neg[k][0].data_ptr() if self._neg else None
+            v.neg_side[k] = self._neg[k][1].data_ptr() if self._neg else None
+        v.step_loss = self._step_loss.data_ptr()
 
     # -- bookkeeping of the reference drivers -------------------------------------------------
     @property
@@ -89,111 +113,76 @@ class RelationView:
         self.kg1.set_neighbours(nb1, self.device)
         self.kg2.set_neighbours(nb2, self.device)
 
-    # -- one step -------------------------------------------------------------------------------
-    def _phase1(self, pos1, len1, pos2, len2):
-        stream = _cabi.current_stream()
-        ev = None
-        if self.phase1_events is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
-        _cabi.check(self._lib.mke_rel_step_sampled(
-            self.ent.c, self.rel.c, pos1, len1, self.kg1.c, pos2, len2, self.kg2.c, self.K,
-            self.seed & (2 ** 64 - 1), self.global_step, None, 1.0, self.loss_acc.data_ptr(), None,
-            self.variant, stream))
-        if ev is not None:
-            ev[1].record()
-            self.phase1_events.append(ev)
-
-    def _sample_into(self, buf, pos1, len1, pos2, len2, step, stream):
-        ne, ns = self._neg[buf]
-        _cabi.check(self._lib.mke_sample_structured(
-            pos1, len1, self.kg1.c, pos2, len2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), step,
-            ne.data_ptr(), ns.data_ptr(), stream))
-
-    def _phase1_presampled(self, buf, pos1, len1, pos2, len2):
-        ne, ns = self._neg[buf]
-        ev = None
-        if self.phase1_events is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
-        _cabi.check(self._lib.mke_rel_step_structured2(
-            self.ent.c, self.rel.c, pos1, len1, pos2, len2, self.K, ne.data_ptr(), ns.data_ptr(), None, 1.0,
-            self.loss_acc.data_ptr(), self.variant, _cabi.current_stream()))
-        if ev is not None:
-            ev[1].record()
-            self.phase1_events.append(ev)
-
-    def _slice_ptrs(self, step_in_epoch):
-        (a1, b1), (a2, b2) = self.step_slices(step_in_epoch)
-        return self.triples1.data_ptr() + 12 * a1, b1 - a1, self.triples2.data_ptr() + 12 * a2, b2 - a2
-
-    def _phase2(self):
-        T.apply_adagrad_pair(self.ent, self.ent.adagrad_slot("relation"), self.lr,
-                             self.rel, self.rel.adagrad_slot("relation"), self.lr)
-
-    def step_resident(self, step_in_epoch, next_step_in_epoch=None):
-        """One training step on positives already in HBM; returns the number of positives.
-        `next_step_in_epoch` (pipelined mode): the step whose negatives are drawn meanwhile."""
-        p1, len1, p2, len2 = self._slice_ptrs(step_in_epoch)
-        if len1 + len2 == 0:
-            return 0
-        if not self.pipelined:
-            self._phase1(p1, len1, p2, len2)
-        else:
-            main = torch.cuda.current_stream()
-            ready = self._ready.pop(self.global_step, None)
-            if ready is None:  # nothing drawn ahead (first step, epoch boundary): draw in line
-                buf = self.global_step & 1
-                self._sample_into(buf, p1, len1, p2, len2, self.global_step, main.cuda_stream)
-            else:
-                buf, ev = ready
-                main.wait_event(ev)
-            self._phase1_presampled(buf, p1, len1, p2, len2)
-            if next_step_in_epoch is not None:
-                q1, m1, q2, m2 = self._slice_ptrs(next_step_in_epoch)
-                if m1 + m2 > 0:
-                    # starts when phase 1 of this step has finished, i.e. overlaps the (HBM-bound)
-                    # apply kernel; the other buffer was last read by the previous step's phase 1
-                    fence = main.record_event()
-                    self._side.wait_event(fence)
-                    self._sample_into(buf ^ 1, q1, m1, q2, m2, self.global_step + 1, self._side.cuda_stream)
-                    self._ready[self.global_step + 1] = (buf ^ 1, self._side.record_event())
-        self._phase2()
-        self.global_step += 1
-        return len1 + len2
-
-    def step_host(self, pos1_pinned, pos2_pinned, staging):
-        """One step whose positives arrive in (pinned) HOST memory, loss read back to the host:
-        what one queue.get() + session.run([loss, optimizer]) of MultiKE_model.py:302-310 costs a
-        caller.  Returns (batch loss, number of positives)."""
-        len1, len2 = pos1_pinned.shape[0], pos2_pinned.shape[0]
-        if len1 + len2 == 0:
-            return 0.0, 0
-        d1, d2 = staging[0][:len1], staging[1][:len2]
-        d1.copy_(pos1_pinned, non_blocking=True)
-        d2.copy_(pos2_pinned, non_blocking=True)
-        self.loss_acc.zero_()
-        self._phase1(d1.data_ptr(), len1, d2.data_ptr(), len2)
-        self._phase2()
-        self.global_step += 1
-        return float(self.loss_acc.item()), len1 + len2
-
-    def make_staging(self):
+    def use_host_triples(self, pinned1=None, pinned2=None):
+        """Host-fed mode: every step's positives are copied from pinned HOST memory (what the
+        reference's queue.get() + feed_dict hands to session.run) and every step's loss is copied
+        back to a pinned host buffer.  Default source: pinned copies of the current lists."""
         b1, b2 = split_batch(self.n1, self.n2, self.batch_size)
-        return (torch.empty(b1, 3, dtype=torch.int32, device=self.device),
-                torch.empty(b2, 3, dtype=torch.int32, device=self.device))
+        p1 = self.triples1.cpu().pin_memory() if pinned1 is None else pinned1
+        p2 = self.triples2.cpu().pin_memory() if pinned2 is None else pinned2
+        assert p1.is_pinned() and p2.is_pinned() and p1.dtype == torch.int32 and p2.dtype == torch.int32
+        self._host_triples = (p1, p2)
+        if self._stage is None:
+            self._stage = [torch.empty(max(b, 1) * 3, dtype=torch.int32, device=self.device)
+                           for b in (b1, b1, b2, b2)]
+
+    # -- steps --------------------------------------------------------------------------------
+    def train_steps(self, first_step, n_steps, host_fed=False):
+        """n_steps consecutive steps starting at step `first_step` of the epoch (wrapping at the
+        epoch end), issued by ONE library call.  Per-step losses are left in self.step_losses
+        (device) and, host-fed, in self.host_losses (pinned).  Returns #positives trained."""
+        if n_steps <= 0:
+            return 0
+        if self._step_loss.numel() < n_steps:
+            self._step_loss = torch.zeros(n_steps, dtype=torch.float64, device=self.device)
+            self._view.step_loss = self._step_loss.data_ptr()
+        self._step_loss[:n_steps].zero_()
+        v = self._view
+        if host_fed:
+            if self._host_triples is None:
+                self.use_host_triples()
+            if self._host_loss is None or self._host_loss.numel() < n_steps:
+                self._host_loss = torch.zeros(n_steps, dtype=torch.float64).pin_memory()
+            v.host_triples1, v.host_triples2 = self._host_triples[0].data_ptr(), self._host_triples[1].data_ptr()
+            v.stage1[0], v.stage1[1] = self._stage[0].data_ptr(), self._stage[1].data_ptr()
+            v.stage2[0], v.stage2[1] = self._stage[2].data_ptr(), self._stage[3].data_ptr()
+            v.host_step_loss = self._host_loss.data_ptr()
+        else:
+            v.host_triples1 = v.host_triples2 = None
+            v.host_step_loss = None
+        main = torch.cuda.current_stream()
+        positives = ctypes.c_int64(0)
+        _cabi.check(self._lib.mke_rel_train_steps(ctypes.byref(v), int(first_step), int(n_steps),
+                                                  self.global_step, ctypes.byref(positives), main.cuda_stream,
+                                                  self._side.cuda_stream))
+        self.global_step += n_steps
+        self._last_steps = n_steps
+        return int(positives.value)
+
+    @property
+    def step_losses(self):
+        """Device tensor [n_steps] of the per-step batch losses of the last train_steps call."""
+        return self._step_loss[: self._last_steps]
+
+    @property
+    def host_losses(self):
+        """Pinned host tensor of the same (host-fed calls); valid after a stream synchronise."""
+        return self._host_loss[: self._last_steps]
+
+    def step_resident(self, step_in_epoch):
+        """One training step on positives already in HBM; returns the number of positives."""
+        return self.train_steps(step_in_epoch, 1)
 
     # -- one epoch ------------------------------------------------------------------------------
-    def train_epoch(self, shuffle=True, generator=None):
-        """train_relation_view_1epo: all steps of one epoch from device-resident triples; the
-        loss stays on the device until the end of the epoch.  Returns (avg loss, #positives)."""
-        self.loss_acc.zero_()
-        trained = 0
-        steps = self.triple_steps
-        for s in range(steps):
-            trained += self.step_resident(s, s + 1 if s + 1 < steps else None)
-        loss = float(self.loss_acc.item())
-        if shuffle:  # MultiKE_model.py:314-315 random.shuffle of both lists
-            self.triples1 = self.triples1[torch.randperm(self.n1, device=self.device, generator=generator)]
-            self.triples2 = self.triples2[torch.randperm(self.n2, device=self.device, generator=generator)]
+    def train_epoch(self, shuffle=True, generator=None, host_fed=False):
+        """train_relation_view_1epo: all steps of one epoch; the losses stay on the device until
+        the end of the epoch.  Returns (avg loss per positive, #positives)."""
+        trained = self.train_steps(0, self.triple_steps, host_fed=host_fed)
+        loss = float(self.step_losses.sum().item())
+        if shuffle:  # MultiKE_model.py:314-315 random.shuffle of both lists (in place: same buffers)
+            self.triples1.copy_(self.triples1[torch.randperm(self.n1, device=self.device, generator=generator)])
+            self.triples2.copy_(self.triples2[torch.randperm(self.n2, device=self.device, generator=generator)])
+            if self._host_triples is not None and host_fed:
+                self._host_triples[0].copy_(self.triples1)
+                self._host_triples[1].copy_(self.triples2)
         return loss / max(trained, 1), trained

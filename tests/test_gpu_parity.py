@@ -286,6 +286,39 @@ def test_structured_sampler_and_pipelined_driver(G, golden):
     assert out[0][0] == pytest.approx(out[1][0], rel=1e-6)
     torch.testing.assert_close(out[0][1], out[1][1], rtol=0, atol=ROW_ATOL)
     torch.testing.assert_close(out[0][2], out[1][2], rtol=0, atol=ROW_ATOL)
+    # host-fed steps (pinned positives in, per-step loss out) give the same again
+    rv = RelationView(2 * n_ent, 5, 75, t1, t2, n_ent, batch_size=200, neg_num=K, lr=0.001, seed=5,
+                      ent_init=ent0, rel_init=rel0, filter1=all1, filter2=all2, pipelined=True)
+    losses = [rv.train_epoch(shuffle=False, host_fed=True)[0] for _ in range(2)]
+    torch.cuda.synchronize()
+    assert losses == pytest.approx(out[0][0], rel=1e-6)
+    assert float(rv.host_losses.sum()) == pytest.approx(float(rv.step_losses.sum().item()), rel=1e-12)
+    torch.testing.assert_close(rv.ent.var, out[0][1], rtol=0, atol=ROW_ATOL)
+    # the oracle agrees with the whole pipeline: dense TF semantics on the negatives the CPU
+    # restatement of the sampler draws, step by step
+    ok1 = ds.KG(entity_base=0, n_entities=n_ent, triples=all1)
+    ok2 = ds.KG(entity_base=n_ent, n_entities=n_ent, triples=all2)
+    oe = orv.DenseTable(ent0.numpy(), True, torch.float64)
+    orl = orv.DenseTable(rel0.numpy(), True, torch.float64)
+    rv = RelationView(2 * n_ent, 5, 75, t1, t2, n_ent, batch_size=200, neg_num=K, lr=0.001, seed=5,
+                      ent_init=ent0, rel_init=rel0, filter1=all1, filter2=all2)
+    tot, npos = 0.0, 0
+    for step in range(rv.triple_steps):
+        (a1, b1), (a2, b2) = rv.step_slices(step)
+        q1, q2 = t1[a1:b1], t2[a2:b2]
+        neg = ds.sample_batch(q1, ok1, q2, ok2, K, 5, step)
+        pos = np.concatenate([q1, q2])
+        loss, _, _ = orv.relation_view_step(oe, orl, pos[:, 0], pos[:, 1], pos[:, 2], neg[:, 0], neg[:, 1], neg[:, 2],
+                                            0.001)
+        tot += loss
+        npos += len(pos)
+    got, trained = rv.train_epoch(shuffle=False)
+    # epoch coverage quirk kept on purpose: B1 = int(700/1200*200) = 116 is floored
+    # while steps = ceil(1200/200) = 6, so 6*116 = 696 of the 700 kg1 triples are visited per epoch
+    assert trained == npos == 696 + 500
+    assert got == pytest.approx(tot / npos, rel=1e-5)
+    np.testing.assert_allclose(rv.ent.raw(), oe.var.numpy(), rtol=0, atol=5 * ROW_ATOL)
+    np.testing.assert_allclose(rv.rel.raw(), orl.var.numpy(), rtol=0, atol=5 * ROW_ATOL)
 
 
 def test_tripleset_membership(G, golden):
