@@ -184,6 +184,23 @@ int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
                                 const mke_table_t* b, float* acc_b, float lr_b, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * losses.py as free functions on already gathered [n, dim] matrices (row stride ld floats).
+ * ------------------------------------------------------------------------------------------ */
+
+/*
+ * loss += scale * sum_i w_i log(1 + exp(+-|H_i + M_i - T_i|^2))  (sign: + positives, - negatives)
+ * and, where the pointers are non-NULL, gH/gM/gT [n, ld] are OVERWRITTEN with d loss / d row.
+ * One call per term of relation_logistic_loss / attribute_logistic_loss / *_wo_negs (losses.py:4-50).
+ */
+int mke_dense_logistic_fwd_bwd(const float* H, const float* M, const float* T, int32_t n, int32_t dim,
+                               int32_t ld, const float* w_or_null, int32_t negative, float scale,
+                               double* loss_accum, float* gH, float* gM, float* gT, mke_stream_t stream);
+
+/* alignment_loss (losses.py:66-69): loss += scale * sum_i |A_i - B_i|^2, gA = 2 scale (A - B), gB = -gA */
+int mke_dense_sqdist_fwd_bwd(const float* A, const float* B, int32_t n, int32_t dim, int32_t ld,
+                             float scale, double* loss_accum, float* gA, float* gB, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Step / epoch driver.
  * ------------------------------------------------------------------------------------------ */
 

@@ -1,0 +1,212 @@
+"""Mirror of code/MultiKE_model.py for the relation view (SURVEY.md section 8 rows a-2 .. a-7, a-11).
+
+Same class name, constructor and method signatures as the reference, so MultiKE_CSL.MultiKE_CV /
+MultiKE_Late.MultiKE_Late style drivers can call it; the TF graph + session.run are replaced by
+device tables and the kernels behind the C-ABI (multike_b200/relation_view.py).  What differs on
+purpose: batches and negatives never leave the device (``steps_tasks`` / ``batch_queue`` are
+accepted and ignored), and the per-epoch print lines are kept verbatim.
+
+Not mirrored yet (SURVEY.md section 8 "next" rows; calling them raises NotImplementedError): the
+attribute-view CNN graphs (MultiKE_model.py:134-151, 172-185, 203-221), common-space learning
+(:225-239) and space mapping (:241-261).
+"""
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+from multike_b200 import _cabi
+from multike_b200 import tables as T
+from multike_b200.relation_view import RelationView
+
+
+def generate_out_folder(out_folder, training_data_path, div_path, method_name):
+    """utils.py:52-57"""
+    path = training_data_path.strip('/').split('/')[-1]
+    folder = out_folder + method_name + '/' + path + "/" + div_path + str(time.strftime("%Y%m%d%H%M%S")) + "/"
+    print("results output folder:", folder)
+    return folder
+
+
+def _triples(lst, with_weight=False):
+    a = np.asarray(lst, dtype=np.float64 if with_weight else np.int64)
+    if a.size == 0:
+        return np.zeros((0, 3), np.int32), np.zeros(0, np.float32)
+    return np.ascontiguousarray(a[:, :3], dtype=np.int32), (a[:, 3].astype(np.float32) if with_weight else None)
+
+
+def _neighbour_matrix(neighbors, rows):
+    """dict entity -> candidate list (base/batch.py:119-150) as an int32 [rows, k] matrix; entities
+    without an entry get -1 in column 0 (fall back to the whole KG, neighbor.get(e, entities_list))."""
+    if not neighbors:
+        return None
+    k = min(len(v) for v in neighbors.values())
+    m = -np.ones((rows, k), dtype=np.int32)
+    for e, cand in neighbors.items():
+        m[e] = np.asarray(cand[:k], dtype=np.int32)
+    return m
+
+
+class MultiKE:
+
+    def __check_args(self):
+        assert self.args.alignment_module == 'swapping'  # for cross-KG inference
+
+    def __init__(self, data, args, attr_align_model):
+        self.predicate_align_model = attr_align_model
+        self.args = args
+        self.__check_args()
+        self.data = data
+        self.kgs = kgs = data.kgs
+        self.kg1 = kgs.kg1
+        self.kg2 = kgs.kg2
+        self.out_folder = generate_out_folder(self.args.output, self.args.training_data, '', self.__class__.__name__)
+        self.session = None  # kept for the drivers' `.eval(session=self.session)` idiom
+        self.device = torch.device(getattr(args, "device", "cuda"))
+        self.seed = int(getattr(args, "seed", 0))
+        _cabi.load()  # no library, no model: there is no CPU path
+
+    # --- variables (MultiKE_model.py:86-107) ---------------------------------------------------
+    def _define_variables(self):
+        n_ent, n_rel, n_attr, dim = self.kgs.entities_num, self.kgs.relations_num, self.kgs.attributes_num, self.args.dim
+        gen = torch.Generator().manual_seed(self.seed)
+        dev = self.device
+        self._init = {name: T.xavier_truncated_normal(rows, dim, gen) for name, rows in
+                      (("rv_ent_embeds", n_ent), ("rel_embeds", n_rel), ("av_ent_embeds", n_ent),
+                       ("attr_embeds", max(n_attr, 1)), ("ent_embeds", n_ent))}
+        value_vectors = getattr(self.data, "value_vectors", None)
+        name_vectors = getattr(self.data, "local_name_vectors", None)
+        self.literal_embeds = None if value_vectors is None else T.EmbeddingTable(
+            len(value_vectors), dim, False, dev, init=np.asarray(value_vectors, np.float32), trainable=False)
+        self.name_embeds = None if name_vectors is None else T.EmbeddingTable(
+            len(name_vectors), dim, False, dev, init=np.asarray(name_vectors, np.float32), trainable=False)
+        self.av_ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["av_ent_embeds"])
+        # False important! (MultiKE_model.py:96-97)
+        self.attr_embeds = T.EmbeddingTable(max(n_attr, 1), dim, False, dev, init=self._init["attr_embeds"])
+        self.ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["ent_embeds"])
+        self.rv_ent_embeds = None  # created with the relation-view graph (they own the triple lists)
+        self.rel_embeds = None
+
+    # --- view-specific graphs ---------------------------------------------------------------
+    def _define_name_view_graph(self):
+        pass
+
+    def _define_relation_view_graph(self):
+        """MultiKE_model.py:114-132"""
+        kg1, kg2 = self.kgs.kg1, self.kgs.kg2
+        t1, _ = _triples(kg1.local_relation_triples_list)
+        t2, _ = _triples(kg2.local_relation_triples_list)
+        # the filter set aliases relation_triples_set and so also holds the swapped sup triples
+        f1, _ = _triples(list(kg1.local_relation_triples_set))
+        f2, _ = _triples(list(kg2.local_relation_triples_set))
+        self._rv = RelationView(
+            self.kgs.entities_num, self.kgs.relations_num, self.args.dim, t1, t2, ent_split=len(kg1.entities_list),
+            batch_size=self.args.batch_size, neg_num=self.args.neg_triple_num, lr=self.args.learning_rate,
+            seed=self.seed, device=self.device, ent_init=self._init["rv_ent_embeds"], rel_init=self._init["rel_embeds"],
+            filter1=f1, filter2=f2, entities1=kg1.entities_list, entities2=kg2.entities_list)
+        self.rv_ent_embeds, self.rel_embeds = self._rv.ent, self._rv.rel
+
+    def _define_cross_kg_name_view_graph(self):
+        pass
+
+    def _define_cross_kg_entity_reference_relation_view_graph(self):
+        """MultiKE_model.py:158-170: 2 * relation_logistic_loss_wo_negs, its own Adagrad slots"""
+        self._ckge_slot = "ckge_relation"
+
+    def _define_cross_kg_relation_reference_graph(self):
+        """MultiKE_model.py:187-201: 2 * logistic_loss_wo_negs (weighted), its own Adagrad slots"""
+        self._ckgp_slot = "ckgp_relation"
+
+    def _not_yet(self, *a, **k):
+        raise NotImplementedError("attribute-view CNN / common-space / space-mapping graphs are SURVEY.md "
+                                  "section 8 'next' rows; not part of the relation-view hot path")
+
+    _define_attribute_view_graph = _not_yet
+    _define_cross_kg_entity_reference_attribute_view_graph = _not_yet
+    _define_cross_kg_attribute_reference_graph = _not_yet
+    _define_common_space_learning_graph = _not_yet
+    _define_space_mapping_graph = _not_yet
+    train_attribute_view_1epo = _not_yet
+    train_cross_kg_entity_inference_attribute_view_1epo = _not_yet
+    train_cross_kg_attribute_inference_1epo = _not_yet
+    train_shared_space_mapping_1epo = _not_yet
+    train_common_space_learning_1epo = _not_yet
+
+    # --- reads (MultiKE_model.py:263-287) ------------------------------------------------------
+    def eval_kg1_ent_embeddings(self):
+        return self.rv_ent_embeds.eval(idx=self.kgs.kg1.entities_list)
+
+    def eval_kg2_ent_embeddings(self):
+        return self.rv_ent_embeds.eval(idx=self.kgs.kg2.entities_list)
+
+    def eval_kg1_useful_ent_embeddings(self):
+        return self.rv_ent_embeds.eval(idx=self.kgs.useful_entities_list1)
+
+    def eval_kg2_useful_ent_embeddings(self):
+        return self.rv_ent_embeds.eval(idx=self.kgs.useful_entities_list2)
+
+    def save(self):
+        """six .npy files as utils.save_embeddings writes them (utils.py:70-91)"""
+        folder = self.out_folder
+        os.makedirs(folder, exist_ok=True)
+        for fname, tab in (("ent_embeds", self.ent_embeds), ("nv_ent_embeds", self.name_embeds),
+                           ("rv_ent_embeds", self.rv_ent_embeds), ("av_ent_embeds", self.av_ent_embeds),
+                           ("rel_embeds", self.rel_embeds), ("attr_embeds", self.attr_embeds)):
+            if tab is not None:
+                np.save(folder + fname + '.npy', tab.eval())
+        print("Embeddings saved!")
+
+    # --- training (MultiKE_model.py:291-317) ---------------------------------------------------
+    def train_relation_view_1epo(self, epoch, triple_steps, steps_tasks, batch_queue, neighbors1, neighbors2):
+        start = time.time()
+        rv = self._rv
+        rv.set_neighbours(_neighbour_matrix(neighbors1, rv.ent.rows), _neighbour_matrix(neighbors2, rv.ent.rows))
+        trained_samples_num = rv.train_steps(0, triple_steps)
+        epoch_loss = float(rv.step_losses.sum().item()) / max(trained_samples_num, 1)
+        # random.shuffle of both lists (:314-315), on the device
+        rv.triples1.copy_(rv.triples1[torch.randperm(rv.n1, device=rv.device)])
+        rv.triples2.copy_(rv.triples2[torch.randperm(rv.n2, device=rv.device)])
+        end = time.time()
+        print('epoch {} of rel. view, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss, end - start))
+        return epoch_loss
+
+    def _positives_only_epoch(self, sup_triples, slot, weighted):
+        """MultiKE_model.py:349-369 / 393-414: `steps` batches of random.sample(sup_triples, B),
+        loss = 2 * [weighted] logistic loss without negatives, Adagrad slots of this graph."""
+        rv = self._rv
+        pos, w = _triples(sup_triples, with_weight=weighted)
+        n = pos.shape[0]
+        steps = int(math.ceil(n / self.args.batch_size))
+        batch_size = self.args.batch_size if steps > 1 else n
+        pos_d = torch.from_numpy(pos).to(rv.device)
+        w_d = None if w is None else torch.from_numpy(w).to(rv.device)
+        acc = T.new_loss_accumulator(rv.device)
+        trained = 0
+        for _ in range(steps):
+            pick = torch.randperm(n, device=rv.device)[:batch_size]  # random.sample: without replacement
+            T.rel_step_structured(rv.ent, rv.rel, pos_d[pick].contiguous(), None, None, 0, acc,
+                                  w=None if w_d is None else w_d[pick].contiguous(), pos_scale=2.0,
+                                  variant=rv.variant)
+            T.apply_adagrad_pair(rv.ent, rv.ent.adagrad_slot(slot), rv.lr, rv.rel, rv.rel.adagrad_slot(slot), rv.lr)
+            trained += batch_size
+        return float(acc.item()) / max(trained, 1)
+
+    def train_cross_kg_entity_inference_relation_view_1epo(self, epoch, sup_triples):
+        if len(sup_triples) == 0:
+            return
+        start = time.time()
+        epoch_loss = self._positives_only_epoch(sup_triples, self._ckge_slot, weighted=False)
+        print('epoch {} of cross-kg entity inference in rel. view, avg. loss: {:.4f}, time: {:.4f}s'.format(
+            epoch, epoch_loss, time.time() - start))
+        return epoch_loss
+
+    def train_cross_kg_relation_inference_1epo(self, epoch, sup_triples):
+        if len(sup_triples) == 0:
+            return
+        start = time.time()
+        epoch_loss = self._positives_only_epoch(sup_triples, self._ckgp_slot, weighted=True)
+        print('epoch {} of cross-kg relation inference in rel. view, avg. loss: {:.4f}, time: {:.4f}s'.format(
+            epoch, epoch_loss, time.time() - start))
+        return epoch_loss

@@ -41,7 +41,7 @@ class RelationView:
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size=5000, neg_num=10,
                  lr=0.001, seed=0, device="cuda", variant=0, ent_init=None, rel_init=None,
-                 filter1=None, filter2=None, generator=None, pipelined=True):
+                 filter1=None, filter2=None, generator=None, pipelined=True, entities1=None, entities2=None):
         self._lib = _cabi.load()
         self.device = torch.device(device)
         self.dim, self.batch_size, self.K, self.lr = int(dim), int(batch_size), int(neg_num), float(lr)
@@ -61,9 +61,9 @@ class RelationView:
         # filter set = relation_triples_set incl. swapped sup triples (base/kg.py:59,134)
         self.set1 = T.TripleSet(t1 if filter1 is None else filter1, device)
         self.set2 = T.TripleSet(t2 if filter2 is None else filter2, device)
-        self.kg1 = T.KGSampler(entity_base=0, n_entities=ent_split, triple_set=self.set1, device=device)
-        self.kg2 = T.KGSampler(entity_base=ent_split, n_entities=n_ent - ent_split, triple_set=self.set2,
-                               device=device)
+        # candidate pools = kg.entities_list (base/batch.py:40-41); a contiguous id range needs no list
+        self.kg1 = self._pool(entities1, 0, ent_split, self.set1)
+        self.kg2 = self._pool(entities2, ent_split, n_ent - ent_split, self.set2)
         self.global_step = 0
         # Negatives of step s+1 are drawn on a second stream while step s trains: sampling reads
         # no embedding table (only triples, the filter set and the counter-based RNG), so it has
@@ -81,6 +81,15 @@ class RelationView:
         self._stage = None
         self._view = _cabi.MkeRelView()
         self._fill_view()
+
+    def _pool(self, entities, base, count, triple_set):
+        if entities is not None:
+            e = np.asarray(entities, dtype=np.int64)
+            if e.size and np.array_equal(e, np.arange(e[0], e[0] + e.size)):
+                base, count, entities = int(e[0]), int(e.size), None
+        if entities is None:
+            return T.KGSampler(entity_base=base, n_entities=count, triple_set=triple_set, device=self.device)
+        return T.KGSampler(entity_list=entities, triple_set=triple_set, device=self.device)
 
     # -- C view -----------------------------------------------------------------------------
     def _fill_view(self):

@@ -1,0 +1,157 @@
+"""The host-side mirror of the reference's operator surface (multike_b200/refapi): losses.py as
+free differentiable functions and the relation-view part of class MultiKE, against the oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import device_sampler as ds
+from oracle import losses as ol
+from oracle import relation_view as orv
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(n, d, seed, scale=0.5):
+    return torch.tensor(np.random.default_rng(seed).normal(0, scale, (n, d)), dtype=torch.float64)
+
+
+def test_losses_mirror_values_and_gradients():
+    from multike_b200.refapi import losses as ml
+    n, d = 37, 75
+    mats = [_rand(n, d, s) for s in range(6)]
+    w = torch.tensor(np.random.default_rng(9).choice([1.0, 0.9, 0.5], n))
+    cases = [
+        (ml.relation_logistic_loss, ol.relation_logistic_loss, mats),
+        (ml.attribute_logistic_loss, ol.attribute_logistic_loss, mats[:3] + [w] + mats[3:] + [w]),
+        (ml.relation_logistic_loss_wo_negs, ol.relation_logistic_loss_wo_negs, mats[:3]),
+        (ml.attribute_logistic_loss_wo_negs, ol.attribute_logistic_loss_wo_negs, mats[:3]),
+        (ml.logistic_loss_wo_negs, ol.logistic_loss_wo_negs, mats[:3] + [w]),
+        (ml.alignment_loss, ol.alignment_loss, mats[:2]),
+    ]
+    for mine, oracle, args in cases:
+        ref_in = [a.clone().requires_grad_(a.dim() == 2) for a in args]
+        ref = oracle(*ref_in)
+        ref.backward()
+        dev_in = [a.float().cuda().requires_grad_(a.dim() == 2) for a in args]
+        got = mine(*dev_in)
+        assert got.dim() == 0 and got.dtype == torch.float32
+        (3.0 * got).backward()  # upstream gradient is honoured
+        assert float(got) == pytest.approx(float(ref), rel=1e-5)
+        for a, b in zip(dev_in, ref_in):
+            if b.grad is not None:
+                np.testing.assert_allclose(a.grad.cpu().numpy(), 3.0 * b.grad.numpy(), rtol=1e-4, atol=1e-5)
+    # matmul-based terms
+    eye = torch.eye(d, dtype=torch.float64)
+    M = torch.linalg.qr(_rand(d, d, 20))[0]
+    ref = ol.space_mapping_loss(mats[0], mats[1], M, eye, 2.0)
+    got = ml.space_mapping_loss(mats[0].float().cuda(), mats[1].float().cuda(), M.float().cuda(), eye.float().cuda(), 2.0)
+    assert float(got) == pytest.approx(float(ref), rel=1e-4)
+    assert float(ml.orthogonal_loss(2 * eye.float().cuda(), eye.float().cuda())) == pytest.approx(9.0 * d)
+    with pytest.raises(TypeError):
+        ml.alignment_loss(mats[0].float(), mats[1].float())  # CPU tensors: no fallback
+
+
+def _fake_model(golden, batch_size=200, K=10):
+    g = golden("ref_batch_relation.npz")
+    n_ent = int(g["n_ent"])
+    t1 = [tuple(int(x) for x in r) for r in g["triples1"]]
+    t2 = [tuple(int(x) for x in r) for r in g["triples2"]]
+    sup1 = [tuple(int(x) for x in r) for r in g["sup1"]]
+    sup2 = [tuple(int(x) for x in r) for r in g["sup2"]]
+
+    def kg(trip, sup, lo):
+        k = types.SimpleNamespace()
+        k.local_relation_triples_list = list(trip)
+        k.local_relation_triples_set = set(trip) | set(sup)  # aliasing quirk: sup triples are in the filter set
+        k.entities_list = list(range(lo, lo + n_ent))
+        k.sup_relation_triples_list = list(sup)
+        return k
+
+    kgs = types.SimpleNamespace(kg1=kg(t1, sup1, 0), kg2=kg(t2, sup2, n_ent), entities_num=2 * n_ent, relations_num=5,
+                                attributes_num=3, useful_entities_list1=[0, 3, 5], useful_entities_list2=[41, 42])
+    data = types.SimpleNamespace(kgs=kgs)
+    args = types.SimpleNamespace(alignment_module='swapping', output='/tmp/mke_out/', training_data='x/DBP_toy/', dim=75,
+                                 batch_size=batch_size, neg_triple_num=K, learning_rate=0.001, seed=3)
+    from multike_b200.refapi.MultiKE_model import MultiKE
+    m = MultiKE(data, args, None)
+    m._define_variables()
+    m._define_name_view_graph()
+    m._define_relation_view_graph()
+    m._define_cross_kg_entity_reference_relation_view_graph()
+    m._define_cross_kg_relation_reference_graph()
+    return m, (n_ent, t1, t2, sup1, sup2)
+
+
+def test_multike_relation_view_epochs_match_oracle(golden, capsys):
+    m, (n_ent, t1, t2, sup1, sup2) = _fake_model(golden)
+    K, B = 10, 200
+    ent0, rel0 = m.rv_ent_embeds.raw().astype(np.float64), m.rel_embeds.raw().astype(np.float64)
+    oe, orl = orv.DenseTable(ent0, True, torch.float64), orv.DenseTable(rel0, True, torch.float64)
+    all1, all2 = np.array(t1 + sup1), np.array(t2 + sup2)
+    ok1 = ds.KG(entity_base=0, n_entities=n_ent, triples=all1)
+    ok2 = ds.KG(entity_base=n_ent, n_entities=n_ent, triples=all2)
+    steps = int(np.ceil((len(t1) + len(t2)) / B))
+    # epoch 1 of the relation view: same batches, same draws as the CPU restatement
+    a1, a2 = np.array(t1), np.array(t2)
+    tot, npos = 0.0, 0
+    for step in range(steps):
+        (s1, e1), (s2, e2) = m._rv.step_slices(step)
+        q1, q2 = a1[s1:e1], a2[s2:e2]
+        neg = ds.sample_batch(q1, ok1, q2, ok2, K, 3, step)
+        pos = np.concatenate([q1, q2])
+        loss, _, _ = orv.relation_view_step(oe, orl, pos[:, 0], pos[:, 1], pos[:, 2], neg[:, 0], neg[:, 1], neg[:, 2], 0.001)
+        tot += loss
+        npos += len(pos)
+    got = m.train_relation_view_1epo(1, steps, None, None, None, None)
+    out = capsys.readouterr().out
+    assert "epoch 1 of rel. view, avg. loss: {:.4f}".format(tot / npos) in out
+    assert got == pytest.approx(tot / npos, rel=1e-5)
+    np.testing.assert_allclose(m.rv_ent_embeds.raw(), oe.var.numpy(), rtol=0, atol=1e-5)
+    # cross-KG entity inference (positives only, loss x2, its own Adagrad accumulators): one step
+    # holds all sup triples, so the random order inside the batch does not matter
+    sup = m.kgs.kg1.sup_relation_triples_list + m.kgs.kg2.sup_relation_triples_list
+    m.args.batch_size = len(sup)
+    e = np.zeros(0, np.int64)
+    P = np.array(sup)
+    ref_loss, _, _ = orv.relation_view_step(oe, orl, P[:, 0], P[:, 1], P[:, 2], e, e, e, 0.001, slot="ckge", pos_scale=2.0)
+    got = m.train_cross_kg_entity_inference_relation_view_1epo(1, sup)
+    assert got == pytest.approx(ref_loss / len(sup), rel=1e-5)
+    np.testing.assert_allclose(m.rv_ent_embeds.raw(), oe.var.numpy(), rtol=0, atol=1e-5)
+    # weighted cross-KG relation inference
+    w = np.random.default_rng(0).choice([1.0, 0.8, 0.6], len(sup))
+    supw = [(h, r, t, float(x)) for (h, r, t), x in zip(sup, w)]
+    ref_loss, _, _ = orv.relation_view_step(oe, orl, P[:, 0], P[:, 1], P[:, 2], e, e, e, 0.001, slot="ckgp", pos_w=w,
+                                            pos_scale=2.0)
+    got = m.train_cross_kg_relation_inference_1epo(1, supw)
+    assert got == pytest.approx(ref_loss / len(sup), rel=1e-5)
+    np.testing.assert_allclose(m.rv_ent_embeds.raw(), oe.var.numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(m.rel_embeds.raw(), orl.var.numpy(), rtol=0, atol=1e-5)
+    # reads used by the drivers
+    e1 = m.eval_kg1_ent_embeddings()
+    assert e1.shape == (n_ent, 75) and np.allclose(np.linalg.norm(e1, axis=1), 1.0, atol=1e-5)
+    assert m.eval_kg2_useful_ent_embeddings().shape == (2, 75)
+    assert m.rv_ent_embeds.eval(session=m.session).shape == (2 * n_ent, 75)
+    with pytest.raises(NotImplementedError):
+        m._define_attribute_view_graph()
+
+
+def test_multike_truncated_neighbours_are_used(golden):
+    m, (n_ent, t1, t2, _, _) = _fake_model(golden, batch_size=100, K=5)
+    rng = np.random.default_rng(1)
+    nb1 = {e: [int(x) for x in rng.choice(np.arange(0, n_ent), 12, replace=False)] for e in range(0, n_ent)}
+    nb2 = {e: [int(x) for x in rng.choice(np.arange(n_ent, 2 * n_ent), 12, replace=False)] for e in range(n_ent, 2 * n_ent)}
+    before = m.rv_ent_embeds.raw().copy()
+    loss = m.train_relation_view_1epo(1, m._rv.triple_steps, None, None, nb1, nb2)
+    assert np.isfinite(loss) and loss > 0
+    assert np.abs(m.rv_ent_embeds.raw() - before).max() > 0
+    # the sampler now draws from the 12-entity lists only
+    from multike_b200 import tables as T
+    neg = T.sample_uniform(np.array(t1[:50], np.int32), m._rv.kg1, None, None, 5, 3, 0).cpu().numpy().reshape(-1, 5, 3)
+    for (h, r, t), row in zip(t1[:50], neg):
+        for nh, _, nt in row:
+            assert (nh == h and nt in nb1[t]) or (nt == t and nh in nb1[h])
+    with pytest.raises(AssertionError):
+        from multike_b200.refapi.MultiKE_model import MultiKE
+        MultiKE(m.data, types.SimpleNamespace(alignment_module='mapping', output='', training_data='x'), None)
