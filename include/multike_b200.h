@@ -25,10 +25,11 @@
 extern "C" {
 #endif
 
-#define MKE_ABI_VERSION 2
+#define MKE_ABI_VERSION 3
 #define MKE_EINVAL (-100000)
 #define MKE_MAX_NEG 32        /* K (negatives per positive) supported by the fused kernel */
 #define MKE_MAX_TRY 10        /* base/batch.py:86 max_try=10 */
+#define MKE_MAX_SHARDS 8      /* GPUs of one NVLink/NVSwitch box */
 
 typedef struct CUstream_st* mke_stream_t; /* == cudaStream_t */
 
@@ -55,6 +56,17 @@ typedef struct mke_table {
                           copy blockIdx % R) and phase 2 sums and re-zeroes them.  For small hot
                           tables (rel_embeds: the top relation carries 10-16 % of a batch), where
                           thousands of reductions per step would otherwise serialise on one row  */
+  /* Row sharding over the GPUs of one box.  n_shards in {0,1}: not sharded.
+     n_shards = G in {2,4,8}: `rows` is the GLOBAL row count, row id lives on rank id % G at local
+     row id / G; var/grad/touched above are THIS rank's shard (ceil((rows - rank)/G) rows) and
+     peer_*[k] are the shards of all ranks as mapped into this process (CUDA IPC; peer_*[shard_rank]
+     == var/grad/touched).  Phase 1 gathers rows and reduces gradient rows through these pointers
+     over NVLink; phase 2 runs on the local shard only. */
+  int32_t  n_shards;
+  int32_t  shard_rank;
+  float*   peer_var[MKE_MAX_SHARDS];
+  float*   peer_grad[MKE_MAX_SHARDS];
+  uint8_t* peer_touched[MKE_MAX_SHARDS];
 } mke_table_t;
 
 /*
@@ -288,6 +300,23 @@ int mke_sample_structured(const int32_t* pos1, int32_t len1, const mke_kg_sample
                           const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
                           int32_t K, uint64_t seed, uint64_t step, int32_t* neg_ent,
                           uint32_t* neg_side, mke_stream_t stream);
+
+/* mke_sample_structured for a launch that holds positions [index_base, index_base + len1 + len2)
+ * of a larger (global) batch: the RNG coordinate of local positive i is index_base + i, so the
+ * ranks of a multi-GPU step draw exactly what one GPU would draw for the whole batch. */
+int mke_sample_structured_at(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                             const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                             int32_t K, uint64_t seed, uint64_t step, int32_t index_base,
+                             int32_t* neg_ent, uint32_t* neg_side, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer memory for row-sharded tables (one process per GPU; handles travel over torch.distributed).
+ * ------------------------------------------------------------------------------------------ */
+int mke_peer_alloc(uint64_t bytes, void** ptr);                  /* cudaMalloc + zero fill          */
+int mke_peer_free(void* ptr);
+int mke_ipc_export(const void* ptr, unsigned char handle[64]);   /* cudaIpcGetMemHandle             */
+int mke_ipc_open(const unsigned char handle[64], void** ptr);    /* cudaIpcOpenMemHandle            */
+int mke_ipc_close(void* ptr);
 
 /* ------------------------------------------------------------------------------------------
  * Table utilities.

@@ -11,10 +11,11 @@ from . import build as _build
 
 _c = ctypes
 c_i32p = _c.c_void_p  # device pointers travel as integers
-MKE_ABI_VERSION = 2
+MKE_ABI_VERSION = 3
 MKE_EINVAL = -100000
 MKE_MAX_NEG = 32
 MKE_MAX_TRY = 10
+MKE_MAX_SHARDS = 8
 
 
 class MkeTable(_c.Structure):
@@ -27,6 +28,11 @@ class MkeTable(_c.Structure):
         ("dim", _c.c_int32),
         ("normalised", _c.c_int32),
         ("grad_replicas", _c.c_int32),
+        ("n_shards", _c.c_int32),
+        ("shard_rank", _c.c_int32),
+        ("peer_var", _c.c_void_p * MKE_MAX_SHARDS),
+        ("peer_grad", _c.c_void_p * MKE_MAX_SHARDS),
+        ("peer_touched", _c.c_void_p * MKE_MAX_SHARDS),
     ]
 
 
@@ -89,6 +95,12 @@ SIGNATURES = {
     "mke_tripleset_contains": (_i32, [_PS, _vp, _i32, _vp, _vp]),
     "mke_sample_uniform": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp]),
     "mke_sample_structured": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp, _vp]),
+    "mke_sample_structured_at": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _i32, _vp, _vp, _vp]),
+    "mke_peer_alloc": (_i32, [_u64, _c.POINTER(_c.c_void_p)]),
+    "mke_peer_free": (_i32, [_vp]),
+    "mke_ipc_export": (_i32, [_vp, _c.c_char_p]),
+    "mke_ipc_open": (_i32, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
+    "mke_ipc_close": (_i32, [_vp]),
     "mke_table_export": (_i32, [_PT, _vp, _i32, _vp, _vp]),
     "mke_fill_rows": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp]),
 }

@@ -134,7 +134,8 @@ struct ApplyTable {
   int replicas;  // gradient copies to sum and re-zero (mke_table_t.grad_replicas), >= 1
 };
 static ApplyTable apply_table(const mke_table_t* t, float* acc, float lr) {
-  return ApplyTable{t->var, t->grad, t->touched, acc, t->rows, t->normalised, lr,
+  // a row-sharded table is swept shard by shard: this rank's rows only
+  return ApplyTable{t->var, t->grad, t->touched, acc, table_local_rows(t), t->normalised, lr,
                     t->grad_replicas > 1 ? t->grad_replicas : 1};
 }
 
@@ -284,10 +285,10 @@ static int launch_apply(const mke_table_t* t, float* acc, float lr, cudaStream_t
       per_sm < 1)
     per_sm = 1;
   const int full = sm_count() * per_sm;
-  int need = ((t->rows + 31) / 32 + kApplyWarps - 1) / kApplyWarps;
+  int need = ((table_local_rows(t) + 31) / 32 + kApplyWarps - 1) / kApplyWarps;
   if (need > full) need = full;
   if (need < 1) need = 1;
-  kern<<<need, kApplyThreads, 0, stream>>>(t->var, t->grad, t->touched, acc, t->rows, t->stride,
+  kern<<<need, kApplyThreads, 0, stream>>>(t->var, t->grad, t->touched, acc, table_local_rows(t), t->stride,
                                            (t->dim + 3) / 4, t->normalised, lr,
                                            t->grad_replicas > 1 ? t->grad_replicas : 1);
   MKE_CHECK_LAUNCH("apply_adagrad_kernel");
@@ -327,7 +328,7 @@ extern "C" int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, f
                                            mke_stream_t stream) {
   MKE_CHECK_ARG(a && b, "null table");
   if (a->stride == b->stride && a->var && a->grad && acc_a && b->var && b->grad && acc_b &&
-      a->rows > 0 && b->rows > 0 &&
+      a->rows > 0 && b->rows > 0 && !(a->grad_replicas > 1 && a->n_shards > 1) &&
       (int64_t)a->rows + (int64_t)b->rows < (1ll << 31)) {
     const ApplyTable A = apply_table(a, acc_a, lr_a);
     const ApplyTable B = apply_table(b, acc_b, lr_b);

@@ -37,6 +37,15 @@ int sm_count();
     if (e__ != cudaSuccess) return ::mke::cuda_fail(e__, what);                               \
   } while (0)
 
+// rows of a (possibly row-sharded) table that live on this rank: ids r with r % G == rank
+inline int table_local_rows(const mke_table_t* t) {
+  if (t->n_shards <= 1) return t->rows;
+  return t->rows > t->shard_rank ? (t->rows - t->shard_rank + t->n_shards - 1) / t->n_shards : 0;
+}
+inline int shard_log2(int n_shards) {
+  return n_shards >= 8 ? 3 : n_shards >= 4 ? 2 : n_shards >= 2 ? 1 : 0;
+}
+
 // ---- counter-based RNG (restated bit-exactly in oracle/sampler.py) --------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 30;

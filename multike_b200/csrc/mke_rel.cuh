@@ -4,6 +4,14 @@
 
 namespace mke {
 
+// Row-sharded entity table as phase 1 sees it (mke_table_t.peer_*): row id lives in shard
+// id & (G-1) at local row id >> log2(G).
+struct EntShards {
+  const float* var[MKE_MAX_SHARDS];
+  float* grad[MKE_MAX_SHARDS];
+  uint8_t* touched[MKE_MAX_SHARDS];
+};
+
 struct RelStepParams {
   const float* ent_var;
   float* ent_grad;
@@ -31,6 +39,9 @@ struct RelStepParams {
   float pos_scale;
   double* loss;
   int32_t* neg_out;
+  EntShards sh;             // used when shard_log2 > 0
+  int shard_log2;           // log2(number of entity-table shards); 0 = not sharded
+  int index_base;           // position of this launch's first positive inside its global batch
   unsigned long long* trace;  // debug: per-warp milestone clocks (MKE_TRACE), else NULL
   int dbg;  // timing experiments only (MKE_DEBUG_SKIP): bit0 no rel RED, bit1 no touched, bit2 no loss atomic, bit3 no ent RED, bit4 no hash probe
 };
@@ -44,6 +55,23 @@ __device__ __forceinline__ void softplus_sigmoid(float x, float& sp, float& sg) 
   const float one_p = 1.0f + ex;
   sp = __logf(one_p);
   sg = __fdividef(ex, one_p);
+}
+
+// entity rows: local table, or the owner's shard through its peer mapping
+__device__ __forceinline__ const float* ent_var_row(const RelStepParams& p, int32_t id, int stride) {
+  if (p.shard_log2 == 0) return p.ent_var + (size_t)id * stride;
+  return p.sh.var[id & ((1 << p.shard_log2) - 1)] + (size_t)(id >> p.shard_log2) * stride;
+}
+__device__ __forceinline__ float* ent_grad_row(const RelStepParams& p, int32_t id, int stride) {
+  if (p.shard_log2 == 0) return p.ent_grad + (size_t)id * stride;
+  return p.sh.grad[id & ((1 << p.shard_log2) - 1)] + (size_t)(id >> p.shard_log2) * stride;
+}
+__device__ __forceinline__ void ent_mark(const RelStepParams& p, int32_t id) {
+  if (p.shard_log2 == 0) {
+    mark_touched(p.ent_touched, id);
+  } else {
+    mark_touched(p.sh.touched[id & ((1 << p.shard_log2) - 1)], id >> p.shard_log2);
+  }
 }
 
 // this thread block's copy of the relation gradient table (mke_table_t.grad_replicas)

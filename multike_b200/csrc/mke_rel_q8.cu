@@ -97,18 +97,15 @@ __device__ __forceinline__ float sumsq(const float (&x)[FPL]) {
 // is re-read from the tables and reduced straight into the gradient rows.  Executed by the whole
 // warp (shuffles use the full mask); quarters with on == false compute and discard.
 template <int FPL>
-static __device__ __noinline__ float odd_negative(const float* __restrict__ ent_var,
-                                                  const float* __restrict__ rel_var,
-                                                  float* __restrict__ ent_grad,
-                                                  float* __restrict__ rel_grad, int ent_norm,
-                                                  int rel_norm, int32_t h, int32_t r, int32_t t,
-                                                  int32_t e, bool head_side, bool on, int sub) {
-  constexpr int stride = FPL * 8;
+static __device__ __noinline__ float odd_negative(const float* vh, const float* vr, const float* vt,
+                                                  const float* ve, float* gh, float* gr, float* gt, float* ge,
+                                                  int ent_norm, int rel_norm, bool head_side, bool on,
+                                                  int sub) {
   float xh[FPL], xr[FPL], xt[FPL], xe[FPL];
-  load_row<FPL>(ent_var + (size_t)h * stride, sub, xh);
-  load_row<FPL>(rel_var + (size_t)r * stride, sub, xr);
-  load_row<FPL>(ent_var + (size_t)t * stride, sub, xt);
-  load_row<FPL>(ent_var + (size_t)e * stride, sub, xe);
+  load_row<FPL>(vh, sub, xh);
+  load_row<FPL>(vr, sub, xr);
+  load_row<FPL>(vt, sub, xt);
+  load_row<FPL>(ve, sub, xe);
   float sh = sumsq<FPL>(xh), sr = sumsq<FPL>(xr), st = sumsq<FPL>(xt), se = sumsq<FPL>(xe);
   qsum3(sh, sr, st);
   se = qsum(se);
@@ -128,12 +125,12 @@ static __device__ __noinline__ float odd_negative(const float* __restrict__ ent_
   softplus_sigmoid(-sn, lneg, sg);
   if (!on) return 0.f;
   const float cn = -2.f * sg;
-  red_row<FPL>(rel_grad + (size_t)r * stride, sub, nd, cn);
-  red_row<FPL>(ent_grad + (size_t)e * stride, sub, nd, head_side ? cn : -cn);
+  red_row<FPL>(gr, sub, nd, cn);
+  red_row<FPL>(ge, sub, nd, head_side ? cn : -cn);
   if (head_side)
-    red_row<FPL>(ent_grad + (size_t)t * stride, sub, nd, -cn);
+    red_row<FPL>(gt, sub, nd, -cn);
   else
-    red_row<FPL>(ent_grad + (size_t)h * stride, sub, nd, cn);
+    red_row<FPL>(gh, sub, nd, cn);
   return lneg;
 }
 
@@ -313,9 +310,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
       if (h + r + t == -3) MKE_TRACE(15);  // (forces the id loads to have landed)
       MKE_TRACE(1);
       // the three rows of the positive travel to shared memory while the sampler probes
-      stg.issue(0, p.ent_var + (size_t)h * stride, sub);
+      stg.issue(0, ent_var_row(p, h, stride), sub);
       stg.issue(1, p.rel_var + (size_t)r * stride, sub);
-      stg.issue(2, p.ent_var + (size_t)t * stride, sub);
+      stg.issue(2, ent_var_row(p, t, stride), sub);
       cp_async_commit();
       if (K > 0) {
         if (p.sampled) {
@@ -325,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
             kg.neighbours = nullptr;
             kg.set.slots = nullptr;
           }
-          side = sample_negs_quarter(kg, h, r, t, K, p.skey, (uint32_t)i, lane, pick,
+          side = sample_negs_quarter(kg, h, r, t, K, p.skey, (uint32_t)(p.index_base + i), lane, pick,
                                      p.trace ? p.trace + (size_t)(blockIdx.x * WARPS + wib) * 32 : nullptr);
           if (!valid) {
             side = 0u;
@@ -366,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         // the slots are free again (their contents fed the sums above): first negatives go out
 #pragma unroll
         for (int j = 0; j < kSlots; ++j) {
-          if (j < K) stg.issue(j, p.ent_var + (size_t)pick[j] * stride, sub);
+          if (j < K) stg.issue(j, ent_var_row(p, pick[j], stride), sub);
           cp_async_commit();
         }
         const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
@@ -396,7 +393,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
 #pragma unroll
         for (int k = 0; k < FPL; ++k) acc[k] *= cp;  // d loss / d pd; the K-loop adds the negatives
         // the endpoint that no same-side negative shares gets its positive-term gradient now
-        if (active && !(p.dbg & 8)) out.add(p.ent_grad + (size_t)(side0 ? h : t) * stride, acc, sgn);
+        if (active && !(p.dbg & 8)) out.add(ent_grad_row(p, side0 ? h : t, stride), acc, sgn);
       }
       MKE_TRACE(4);
       // ---- negatives: rows j+1, j+2 are in flight while row j is scored ------------------------
@@ -416,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
           be = fmaf(x[k], base[k], be);
         }
         // slot is free: request row j + kSlots (the sums above consumed x)
-        if (j + kSlots < K) stg.issue(slot, p.ent_var + (size_t)pick[j + kSlots] * stride, sub);
+        if (j + kSlots < K) stg.issue(slot, ent_var_row(p, pick[j + kSlots], stride), sub);
         cp_async_commit();
         slot = (slot + 1 == kSlots) ? 0 : slot + 1;
 #pragma unroll
@@ -438,19 +435,19 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
           x[k] = fmaf(x[k], sie, base[k]);  // neg_distance (losses.py:6)
           acc[k] = fmaf(cn, x[k], acc[k]);
         }
-        if (on && !(p.dbg & 8)) out.add(p.ent_grad + (size_t)e * stride, x, cn * sgn);
+        if (on && !(p.dbg & 8)) out.add(ent_grad_row(p, e, stride), x, cn * sgn);
       }
       cp_async_wait<0>();
       MKE_TRACE(13);
       // ---- r gets every same-side term, the shared endpoint likewise -----------------------
       if (active) {
         if (!(p.dbg & 1)) out.add(rel_grad + (size_t)r * stride, acc, 1.f);
-        if (!(p.dbg & 8)) out.add(p.ent_grad + (size_t)(side0 ? t : h) * stride, acc, -sgn);
+        if (!(p.dbg & 8)) out.add(ent_grad_row(p, side0 ? t : h, stride), acc, -sgn);
         if (!(p.dbg & 2)) {
-        for (int c = sub; c < K; c += 8) mark_touched(p.ent_touched, pick[c]);
+        for (int c = sub; c < K; c += 8) ent_mark(p, pick[c]);
         if (sub == 0) {
-          mark_touched(p.ent_touched, h);
-          mark_touched(p.ent_touched, t);
+          ent_mark(p, h);
+          ent_mark(p, t);
           mark_touched(p.rel_touched, r);
         }
         }
@@ -462,8 +459,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         for (int j = 1; j < K; ++j) {
           const bool odd = active && ((((side >> j) & 1u) != 0u) != side0);
           if (__any_sync(kFull, odd))
-            loss_local += odd_negative<FPL>(p.ent_var, p.rel_var, p.ent_grad, rel_grad, p.ent_norm,
-                                            p.rel_norm, h, r, t, pick[j], !side0, odd, sub);
+            loss_local += odd_negative<FPL>(
+                ent_var_row(p, h, stride), p.rel_var + (size_t)r * stride, ent_var_row(p, t, stride),
+                ent_var_row(p, pick[j], stride), ent_grad_row(p, h, stride), rel_grad + (size_t)r * stride,
+                ent_grad_row(p, t, stride), ent_grad_row(p, pick[j], stride), p.ent_norm, p.rel_norm, !side0,
+                odd, sub);
         }
       }
       __syncwarp();  // pick[] is rewritten by the next positive

@@ -42,7 +42,7 @@ constexpr int kSampWarps = kSampThreads / 32;
 __global__ void __launch_bounds__(kSampThreads)
     sample_kernel(const int32_t* __restrict__ pos1, int len1, mke_kg_sampler_t kg1,
                   const int32_t* __restrict__ pos2, int len2, mke_kg_sampler_t kg2, int K,
-                  uint64_t skey, int32_t* __restrict__ neg_out, int32_t* __restrict__ neg_ent,
+                  uint64_t skey, int index_base, int32_t* __restrict__ neg_out, int32_t* __restrict__ neg_ent,
                   uint32_t* __restrict__ neg_side) {
   __shared__ int32_t s_pick_all[kSampWarps][kQPerWarp][kPickStride];
   const int lane = threadIdx.x & 31;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kSampThreads)
       const int32_t* row = first ? pos1 + 3 * (size_t)i : pos2 + 3 * (size_t)(i - len1);
       const int32_t h = __ldg(row), r = __ldg(row + 1), t = __ldg(row + 2);
       const KgView kg = kg_view(kg1, kg2, first);
-      const uint32_t side = sample_negs_quarter(kg, h, r, t, K, skey, (uint32_t)i, lane, pick);
+      const uint32_t side = sample_negs_quarter(kg, h, r, t, K, skey, (uint32_t)(index_base + i), lane, pick);
       for (int c = sub; c < K; c += 8) {
         const int32_t e = pick[c];
         if (neg_ent != nullptr) neg_ent[(size_t)i * K + c] = e;
@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(kSampThreads)
 
 static int launch_sample(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
                          const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2, int32_t K,
-                         uint64_t seed, uint64_t step, int32_t* neg_out, int32_t* neg_ent,
+                         uint64_t seed, uint64_t step, int32_t index_base, int32_t* neg_out, int32_t* neg_ent,
                          uint32_t* neg_side, cudaStream_t stream) {
+  MKE_CHECK_ARG(index_base >= 0 && (long long)index_base + len1 + len2 < (1ll << 31), "bad index_base");
   MKE_CHECK_ARG(K >= 1 && K <= MKE_MAX_NEG, "K=%d outside [1,%d]", K, MKE_MAX_NEG);
   MKE_CHECK_ARG(len1 >= 0 && len2 >= 0, "negative batch length");
   MKE_CHECK_ARG(len1 == 0 || (pos1 && kg1), "kg1 slice needs positives and a sampler");
@@ -102,7 +103,7 @@ static int launch_sample(const int32_t* pos1, int32_t len1, const mke_kg_sampler
   const int full = sm_count() * 16;
   if (blocks > full) blocks = full;
   sample_kernel<<<blocks, kSampThreads, 0, stream>>>(pos1, len1, a, pos2, len2, b, K, stream_key(seed, step),
-                                                     neg_out, neg_ent, neg_side);
+                                                     index_base, neg_out, neg_ent, neg_side);
   MKE_CHECK_LAUNCH("sample_kernel");
   return 0;
 }
@@ -148,7 +149,7 @@ extern "C" int mke_sample_uniform(const int32_t* pos1, int32_t len1, const mke_k
                                   int32_t K, uint64_t seed, uint64_t step, int32_t* neg_out,
                                   mke_stream_t stream) {
   MKE_CHECK_ARG(neg_out || len1 + len2 == 0, "neg_out is null");
-  return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, neg_out, nullptr, nullptr,
+  return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, 0, neg_out, nullptr, nullptr,
                        (cudaStream_t)stream);
 }
 
@@ -156,7 +157,14 @@ extern "C" int mke_sample_structured(const int32_t* pos1, int32_t len1, const mk
                                      const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
                                      int32_t K, uint64_t seed, uint64_t step, int32_t* neg_ent,
                                      uint32_t* neg_side, mke_stream_t stream) {
+  return mke_sample_structured_at(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, 0, neg_ent, neg_side, stream);
+}
+
+extern "C" int mke_sample_structured_at(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                                        const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                                        int32_t K, uint64_t seed, uint64_t step, int32_t index_base,
+                                        int32_t* neg_ent, uint32_t* neg_side, mke_stream_t stream) {
   MKE_CHECK_ARG((neg_ent && neg_side) || len1 + len2 == 0, "neg_ent/neg_side are null");
-  return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, nullptr, neg_ent, neg_side,
+  return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, index_base, nullptr, neg_ent, neg_side,
                        (cudaStream_t)stream);
 }

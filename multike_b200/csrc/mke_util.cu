@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include "mke_common.cuh"
 
 namespace mke {
@@ -34,14 +35,18 @@ int sm_count() {
 }
 
 // out[i, 0:dim] = l2_normalize(var[idx[i]]) -- one warp per row
-__global__ void table_export_kernel(const float* __restrict__ var, int stride, int dim,
+struct ExportShards {
+  const float* var[MKE_MAX_SHARDS];
+  int log2g;  // 0: var[0] is the whole table
+};
+__global__ void table_export_kernel(ExportShards sh, int stride, int dim,
                                     int normalised, const int32_t* __restrict__ idx, int n,
                                     float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     const int row = idx ? __ldg(idx + i) : i;
-    const float* pv = var + (size_t)row * stride;
+    const float* pv = sh.var[row & ((1 << sh.log2g) - 1)] + (size_t)(row >> sh.log2g) * stride;
     float ss = 0.f;
     for (int c = lane; c < dim; c += 32) {
       const float x = pv[c];
@@ -76,8 +81,17 @@ extern "C" int mke_table_export(const mke_table_t* table, const int32_t* idx_or_
   int blocks = (n + 7) / 8;
   const int full = sm_count() * 8;
   if (blocks > full) blocks = full;
+  ExportShards sh{};
+  sh.var[0] = table->var;
+  if (table->n_shards > 1) {
+    sh.log2g = shard_log2(table->n_shards);
+    for (int k = 0; k < table->n_shards; ++k) {
+      MKE_CHECK_ARG(table->peer_var[k], "peer pointer %d is null", k);
+      sh.var[k] = table->peer_var[k];
+    }
+  }
   table_export_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      table->var, table->stride, table->dim, table->normalised, idx_or_null, n, out);
+      sh, table->stride, table->dim, table->normalised, idx_or_null, n, out);
   MKE_CHECK_LAUNCH("table_export_kernel");
   return 0;
 }
@@ -92,5 +106,39 @@ extern "C" int mke_fill_rows(float* buf, int32_t rows, int32_t stride, int32_t d
   if (blocks > full) blocks = full;
   fill_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(buf, total, stride, dim, value);
   MKE_CHECK_LAUNCH("fill_rows_kernel");
+  return 0;
+}
+
+// ---- peer memory (row-sharded tables): plain cudaMalloc so that the block can be exported ------
+extern "C" int mke_peer_alloc(uint64_t bytes, void** ptr) {
+  MKE_CHECK_ARG(ptr && bytes > 0, "bad peer_alloc arguments");
+  if (cudaError_t e = cudaMalloc(ptr, bytes)) return cuda_fail(e, "cudaMalloc");
+  if (cudaError_t e = cudaMemset(*ptr, 0, bytes)) return cuda_fail(e, "cudaMemset");
+  return 0;
+}
+extern "C" int mke_peer_free(void* ptr) {
+  if (ptr == nullptr) return 0;
+  if (cudaError_t e = cudaFree(ptr)) return cuda_fail(e, "cudaFree");
+  return 0;
+}
+extern "C" int mke_ipc_export(const void* ptr, unsigned char handle[64]) {
+  MKE_CHECK_ARG(ptr && handle, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  if (cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr))) return cuda_fail(e, "cudaIpcGetMemHandle");
+  memcpy(handle, &h, 64);
+  return 0;
+}
+extern "C" int mke_ipc_open(const unsigned char handle[64], void** ptr) {
+  MKE_CHECK_ARG(ptr && handle, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  if (cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess))
+    return cuda_fail(e, "cudaIpcOpenMemHandle");
+  return 0;
+}
+extern "C" int mke_ipc_close(void* ptr) {
+  if (ptr == nullptr) return 0;
+  if (cudaError_t e = cudaIpcCloseMemHandle(ptr)) return cuda_fail(e, "cudaIpcCloseMemHandle");
   return 0;
 }

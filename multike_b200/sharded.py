@@ -1,0 +1,261 @@
+"""Multi-GPU relation view: one process per GPU of one NVLink/NVSwitch box.
+
+  * the entity table (variable, gradient accumulator, touched flags, Adagrad slots) is ROW-SHARDED:
+    row id lives on rank id % G at local row id // G.  Every rank maps every shard into its own
+    address space (CUDA IPC, mke_ipc_*), and phase 1 gathers rows / reduces gradient rows straight
+    through those peer pointers over NVLink -- the exchange is fused into the kernel, there is no
+    all-to-all;
+  * the relation table is small and dense: replicated, its gradient bucket is summed with an NCCL
+    all-reduce between phase 1 and phase 2 (that collective is also the point after which every
+    rank's peer reductions have landed);
+  * a global step of G * batch_size positives is split by position: rank k trains positions
+    [k n / G, (k+1) n / G) of the concatenated (kg1 slice ++ kg2 slice) batch and draws its
+    negatives at RNG coordinate index_base + i, so G ranks draw what one GPU would draw for the
+    whole batch: the result equals a single-GPU run with batch_size G * B up to fp32 summation order.
+
+The pure index arithmetic lives in module-level functions so that it is testable on CPU (gloo).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import tables as T
+from .relation_view import clipped_slice, split_batch
+
+# ---------------------------------------------------------------------------------------------
+# index arithmetic (CPU-testable)
+# ---------------------------------------------------------------------------------------------
+
+
+def shard_owner(ids, world):
+    ids = np.asarray(ids)
+    return ids % world, ids // world
+
+
+def local_rows(rows, rank, world):
+    return (rows - rank + world - 1) // world if rows > rank else 0
+
+
+def rank_range(n, rank, world):
+    """positions of a batch of n positives trained by `rank`"""
+    return rank * n // world, (rank + 1) * n // world
+
+
+def rank_parts(n1, n2, global_batch, step, rank, world):
+    """((start1, len1), (start2, len2), index_base): the pieces of the kg1 / kg2 triple lists that
+    `rank` trains in global step `step`, and the position of its first positive in the global batch."""
+    b1, b2 = split_batch(n1, n2, global_batch)
+    a1, e1 = clipped_slice(n1, b1, step)
+    a2, e2 = clipped_slice(n2, b2, step)
+    len1, len2 = e1 - a1, e2 - a2
+    lo, hi = rank_range(len1 + len2, rank, world)
+    s1, t1 = min(lo, len1), min(hi, len1)
+    s2, t2 = max(lo, len1) - len1, max(hi, len1) - len1
+    return (a1 + s1, t1 - s1), (a2 + s2, t2 - s2), lo
+
+
+# ---------------------------------------------------------------------------------------------
+# peer memory
+# ---------------------------------------------------------------------------------------------
+
+
+class _DevView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerBuffer:
+    """A cudaMalloc'ed block that every rank of the box can address (CUDA IPC)."""
+
+    def __init__(self, shape, dtype, group):
+        import torch.distributed as dist
+        lib = _cabi.load()
+        self.shape, self.dtype = tuple(shape), dtype
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        nbytes = max(int(np.prod(shape)) * itemsize, 256)
+        p = ctypes.c_void_p()
+        _cabi.check(lib.mke_peer_alloc(nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+        typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+        self._view = _DevView(self.ptr, self.shape, typestr)
+        self.tensor = torch.as_tensor(self._view, device="cuda")
+        handle = ctypes.create_string_buffer(64)
+        _cabi.check(lib.mke_ipc_export(self.ptr, handle))
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peers = []
+        for k in range(world):
+            if k == rank:
+                self.peers.append(self.ptr)
+            else:
+                q = ctypes.c_void_p()
+                _cabi.check(lib.mke_ipc_open(handles[k], ctypes.byref(q)))
+                self.peers.append(q.value)
+        self._rank = rank
+
+    def close(self):
+        lib = _cabi.load()
+        for k, q in enumerate(self.peers):
+            if k != self._rank and q:
+                lib.mke_ipc_close(q)
+        self.peers = []
+
+
+class ShardedEmbeddingTable:
+    """mke_table_t with n_shards = world: this rank's rows of a row-sharded normalised table."""
+
+    def __init__(self, rows, dim, normalised, group, init=None, name=""):
+        import torch.distributed as dist
+        self.rows, self.dim, self.normalised, self.name = int(rows), int(dim), bool(normalised), name
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert self.world in (2, 4, 8), "row sharding supports 2, 4 or 8 ranks"
+        self.stride = T.padded_stride(dim)
+        self.local_rows = local_rows(self.rows, self.rank, self.world)
+        # every shard gets the same (maximal) allocation so that peer offsets never overrun
+        alloc_rows = local_rows(self.rows, 0, self.world)
+        self._bufs = [PeerBuffer((alloc_rows, self.stride), torch.float32, group),
+                      PeerBuffer((alloc_rows, self.stride), torch.float32, group),
+                      PeerBuffer((alloc_rows,), torch.uint8, group)]
+        self.var, self.grad, self.touched = (b.tensor for b in self._bufs)
+        self.device = self.var.device
+        if init is not None:  # init is the GLOBAL [rows, dim] table; keep rows rank, rank + world, ...
+            src = torch.as_tensor(np.asarray(init, dtype=np.float32)) if not torch.is_tensor(init) else init
+            mine = src[self.rank::self.world].to(self.device, torch.float32)
+            self.var[: mine.shape[0], : self.dim] = mine
+        self._slots = {}
+        c = _cabi.MkeTable(var=self.var.data_ptr(), grad=self.grad.data_ptr(), touched=self.touched.data_ptr(),
+                           rows=self.rows, stride=self.stride, dim=self.dim, normalised=int(self.normalised),
+                           grad_replicas=1, n_shards=self.world, shard_rank=self.rank)
+        for k in range(self.world):
+            c.peer_var[k], c.peer_grad[k], c.peer_touched[k] = (b.peers[k] for b in self._bufs)
+        self._c = c
+        self.grad_replicas = 1
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    @property
+    def c(self):
+        return ctypes.byref(self._c)
+
+    def adagrad_slot(self, slot):
+        acc = self._slots.get(slot)
+        if acc is None:
+            acc = torch.full((max(self.var.shape[0], 1), self.stride), T.ADAGRAD_INIT, dtype=torch.float32,
+                             device=self.device)
+            self._slots[slot] = acc
+        return acc
+
+    def grad_sum(self):
+        return self.grad
+
+    def export(self, idx=None):
+        """normalised rows by GLOBAL id (peer reads)"""
+        lib = _cabi.load()
+        if idx is None:
+            idx = np.arange(self.rows, dtype=np.int32)
+        idx_t = torch.as_tensor(np.asarray(idx, dtype=np.int32)).to(self.device).contiguous()
+        out = torch.empty(idx_t.numel(), self.dim, dtype=torch.float32, device=self.device)
+        _cabi.check(lib.mke_table_export(self.c, idx_t.data_ptr(), idx_t.numel(), out.data_ptr(),
+                                         _cabi.current_stream()))
+        return out
+
+    def eval(self, session=None, idx=None):
+        return self.export(idx).cpu().numpy()
+
+    def raw_local(self):
+        return self.var[: self.local_rows, : self.dim].detach().cpu().numpy()
+
+    def close(self):
+        for b in self._bufs:
+            b.close()
+
+
+class ShardedRelationView:
+    """The relation view on G GPUs; every rank constructs it with the same arguments."""
+
+    SLOT = "relation"
+
+    def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size, neg_num, lr, seed, group,
+                 ent_init=None, rel_init=None, filter1=None, filter2=None, rel_replicas=1):
+        import torch.distributed as dist
+        self._lib = _cabi.load()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dim, self.K, self.lr, self.seed = int(dim), int(neg_num), float(lr), int(seed)
+        self.batch_size = int(batch_size)              # per rank
+        self.global_batch = self.batch_size * self.world
+        self.ent = ShardedEmbeddingTable(n_ent, dim, True, group, init=ent_init, name="rv_ent_embeds")
+        self.rel = T.EmbeddingTable(n_rel, dim, True, self.device, init=rel_init, name="rel_embeds", flags=False,
+                                    grad_replicas=rel_replicas)
+        t1 = np.ascontiguousarray(triples1, dtype=np.int32).reshape(-1, 3)
+        t2 = np.ascontiguousarray(triples2, dtype=np.int32).reshape(-1, 3)
+        self.triples1, self.triples2 = torch.from_numpy(t1).to(self.device), torch.from_numpy(t2).to(self.device)
+        self.n1, self.n2 = t1.shape[0], t2.shape[0]
+        self.set1 = T.TripleSet(t1 if filter1 is None else filter1, self.device)
+        self.set2 = T.TripleSet(t2 if filter2 is None else filter2, self.device)
+        self.kg1 = T.KGSampler(entity_base=0, n_entities=ent_split, triple_set=self.set1, device=self.device)
+        self.kg2 = T.KGSampler(entity_base=ent_split, n_entities=n_ent - ent_split, triple_set=self.set2,
+                               device=self.device)
+        cap = self.batch_size + 1
+        self._neg_ent = torch.empty(cap * max(self.K, 1), dtype=torch.int32, device=self.device)
+        self._neg_side = torch.empty(cap, dtype=torch.int32, device=self.device)
+        self.loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._fence = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.global_step = 0
+        self.phase1_events = None
+
+    @property
+    def triple_steps(self):
+        return int(math.ceil((self.n1 + self.n2) / self.global_batch))
+
+    def step(self, step_in_epoch):
+        """one global step; returns the number of positives this rank trained"""
+        import torch.distributed as dist
+        (a1, l1), (a2, l2), base = rank_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank, self.world)
+        stream = _cabi.current_stream()
+        p1 = self.triples1.data_ptr() + 12 * a1
+        p2 = self.triples2.data_ptr() + 12 * a2
+        if l1 + l2 > 0:
+            if self.K > 0:
+                _cabi.check(self._lib.mke_sample_structured_at(
+                    p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), self.global_step, base,
+                    self._neg_ent.data_ptr(), self._neg_side.data_ptr(), stream))
+            ev = None
+            if self.phase1_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            _cabi.check(self._lib.mke_rel_step_structured2(
+                self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent.data_ptr(), self._neg_side.data_ptr(),
+                None, 1.0, self.loss_acc.data_ptr(), 0, stream))
+            if ev is not None:
+                ev[1].record()
+                self.phase1_events.append(ev)
+        # dense gradient bucket of the replicated relation table; after it, every rank's phase 1
+        # (and with it every peer reduction into this rank's shard) has completed
+        dist.all_reduce(self.rel.grad, group=self.group)
+        T.apply_adagrad_pair(self.ent, self.ent.adagrad_slot(self.SLOT), self.lr,
+                             self.rel, self.rel.adagrad_slot(self.SLOT), self.lr)
+        # no rank may start the next phase 1 (peer reads of var, peer reductions into grad) before
+        # every rank has finished this phase 2: a stream-ordered one-element all-reduce (no host sync)
+        dist.all_reduce(self._fence, group=self.group)
+        self.global_step += 1
+        return l1 + l2
+
+    def train_epoch(self):
+        import torch.distributed as dist
+        self.loss_acc.zero_()
+        trained = 0
+        for s in range(self.triple_steps):
+            trained += self.step(s)
+        tot = torch.cat([self.loss_acc, torch.tensor([float(trained)], dtype=torch.float64, device=self.device)])
+        dist.all_reduce(tot, group=self.group)
+        return float(tot[0]) / max(float(tot[1]), 1.0), int(tot[1])
+
+    def close(self):
+        self.ent.close()
