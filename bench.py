@@ -220,8 +220,9 @@ def run_sharded(args, rank, world, local_rank):
                        "triples": int(sv.n1 + sv.n2), "dim": dim, "batch": B, "global_batch": B * world, "neg": K,
                        "steps_per_epoch": spe, "variant": "q8_ldg_red",
                        "l2": "no flush: per-rank working set exceeds L2 / rows come over NVLink",
-                       "parallelism": "entity table row-sharded over %d GPUs (peer gathers + peer reductions inside "
-                                      "phase 1), relation gradients NCCL all-reduced" % world},
+                       "parallelism": "entity table row-sharded over %d GPUs, KG-block placement (each KG on half of "
+                                      "the ranks, positives trained where their rows live; peer gathers + peer "
+                                      "reductions inside phase 1), relation gradients NCCL all-reduced" % world},
             "clocks": clk,
             # the multi-GPU driver keeps the triple lists resident; the host-fed path is the N=1 line
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -64,6 +64,14 @@ typedef struct mke_table {
      over NVLink; phase 2 runs on the local shard only. */
   int32_t  n_shards;
   int32_t  shard_rank;
+  int32_t  shard_split; /* 0: plain id % G placement (above).  S > 0: KG-block placement for the two
+                          KGs of an alignment task (ids [0,S) = KG1, [S,rows) = KG2; relation triples
+                          never cross KGs, base/batch.py:40-41): KG1 rows live on ranks [0,G/2) at
+                          rank id % (G/2), local row id / (G/2); KG2 rows on ranks [G/2,G) likewise
+                          with id - S.  With G = 2 every rank owns one KG and the relation view
+                          needs no peer traffic at all; with G = 4/8 only (G/2-1)/(G/2) of the rows
+                          of a positive are remote instead of (G-1)/G.                           */
+  int32_t  shard_pad;
   float*   peer_var[MKE_MAX_SHARDS];
   float*   peer_grad[MKE_MAX_SHARDS];
   uint8_t* peer_touched[MKE_MAX_SHARDS];

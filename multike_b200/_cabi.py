@@ -30,6 +30,8 @@ class MkeTable(_c.Structure):
         ("grad_replicas", _c.c_int32),
         ("n_shards", _c.c_int32),
         ("shard_rank", _c.c_int32),
+        ("shard_split", _c.c_int32),
+        ("shard_pad", _c.c_int32),
         ("peer_var", _c.c_void_p * MKE_MAX_SHARDS),
         ("peer_grad", _c.c_void_p * MKE_MAX_SHARDS),
         ("peer_touched", _c.c_void_p * MKE_MAX_SHARDS),

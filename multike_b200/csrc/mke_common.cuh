@@ -40,7 +40,36 @@ int sm_count();
 // rows of a (possibly row-sharded) table that live on this rank: ids r with r % G == rank
 inline int table_local_rows(const mke_table_t* t) {
   if (t->n_shards <= 1) return t->rows;
-  return t->rows > t->shard_rank ? (t->rows - t->shard_rank + t->n_shards - 1) / t->n_shards : 0;
+  auto part = [](int rows, int r, int g) { return rows > r ? (rows - r + g - 1) / g : 0; };
+  if (t->shard_split <= 0) return part(t->rows, t->shard_rank, t->n_shards);
+  const int half = t->n_shards / 2;  // KG-block placement
+  return t->shard_rank < half ? part(t->shard_split, t->shard_rank, half)
+                              : part(t->rows - t->shard_split, t->shard_rank - half, half);
+}
+// Placement of a row id (device + host): shard index and local row.  log2g = log2 of the number
+// of ranks an id is spread over (G, or G/2 per KG with split > 0).
+struct ShardMap {
+  int log2g;
+  int split;  // 0 => plain id % G
+  __host__ __device__ __forceinline__ void locate(int32_t id, int& shard, int32_t& local) const {
+    const int m = (1 << log2g) - 1;
+    if (split <= 0) {
+      shard = id & m;
+      local = id >> log2g;
+    } else {
+      const bool second = id >= split;
+      const int32_t x = second ? id - split : id;
+      shard = (second ? (1 << log2g) : 0) | (x & m);
+      local = x >> log2g;
+    }
+  }
+};
+inline ShardMap shard_map(const mke_table_t* t) {
+  ShardMap m;
+  m.split = t->shard_split > 0 ? t->shard_split : 0;
+  const int spread = m.split > 0 ? t->n_shards / 2 : t->n_shards;
+  m.log2g = spread >= 8 ? 3 : spread >= 4 ? 2 : spread >= 2 ? 1 : 0;
+  return m;
 }
 inline int shard_log2(int n_shards) {
   return n_shards >= 8 ? 3 : n_shards >= 4 ? 2 : n_shards >= 2 ? 1 : 0;

@@ -468,6 +468,7 @@ static int validate_tables(const mke_table_t* ent, const mke_table_t* rel) {
   if (ent->n_shards > 1) {
     MKE_CHECK_ARG(ent->n_shards == 2 || ent->n_shards == 4 || ent->n_shards == 8, "n_shards must be 2, 4 or 8");
     MKE_CHECK_ARG(ent->shard_rank >= 0 && ent->shard_rank < ent->n_shards, "bad shard_rank");
+    MKE_CHECK_ARG(ent->shard_split >= 0 && ent->shard_split <= ent->rows, "bad shard_split");
     for (int k = 0; k < ent->n_shards; ++k)
       MKE_CHECK_ARG(ent->peer_var[k] && ent->peer_grad[k], "peer pointer %d of the sharded entity table is null", k);
   }
@@ -520,7 +521,7 @@ static int launch_rel(RelStepParams& p, int variant, cudaStream_t stream) {
     const int rc = launch_rel_q8(p, stream);
     if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = no instantiation for this stride
   }
-  MKE_CHECK_ARG(p.shard_log2 == 0, "row-sharded entity tables need the quarter-warp kernel (variant 0, stride 32/64/80/104/128)");
+  MKE_CHECK_ARG(!p.sharded, "row-sharded entity tables need the quarter-warp kernel (variant 0, stride 32/64/80/104/128)");
   if (variant == 1) {
     const size_t smem = (size_t)kTmaWarps * 4 * (3 + p.K) * p.stride * sizeof(float);
     if (smem <= 200 * 1024) {
@@ -557,7 +558,8 @@ static void fill_tables(RelStepParams& p, const mke_table_t* ent, const mke_tabl
   p.ent_touched = ent->touched;
   p.rel_var = rel->var;
   p.rel_grad = rel->grad;
-  p.shard_log2 = ent->n_shards > 1 ? shard_log2(ent->n_shards) : 0;
+  p.sharded = ent->n_shards > 1 ? 1 : 0;
+  p.smap = shard_map(ent);
   for (int k = 0; k < MKE_MAX_SHARDS; ++k) {
     const bool on = ent->n_shards > 1 && k < ent->n_shards;
     p.sh.var[k] = on ? ent->peer_var[k] : nullptr;

@@ -39,8 +39,9 @@ struct RelStepParams {
   float pos_scale;
   double* loss;
   int32_t* neg_out;
-  EntShards sh;             // used when shard_log2 > 0
-  int shard_log2;           // log2(number of entity-table shards); 0 = not sharded
+  EntShards sh;             // used when sharded != 0
+  ShardMap smap;            // placement of an entity id (mke_table_t.n_shards / shard_split)
+  int sharded;              // 0 = one local table
   int index_base;           // position of this launch's first positive inside its global batch
   unsigned long long* trace;  // debug: per-warp milestone clocks (MKE_TRACE), else NULL
   int dbg;  // timing experiments only (MKE_DEBUG_SKIP): bit0 no rel RED, bit1 no touched, bit2 no loss atomic, bit3 no ent RED, bit4 no hash probe
@@ -59,18 +60,27 @@ __device__ __forceinline__ void softplus_sigmoid(float x, float& sp, float& sg) 
 
 // entity rows: local table, or the owner's shard through its peer mapping
 __device__ __forceinline__ const float* ent_var_row(const RelStepParams& p, int32_t id, int stride) {
-  if (p.shard_log2 == 0) return p.ent_var + (size_t)id * stride;
-  return p.sh.var[id & ((1 << p.shard_log2) - 1)] + (size_t)(id >> p.shard_log2) * stride;
+  if (!p.sharded) return p.ent_var + (size_t)id * stride;
+  int s;
+  int32_t l;
+  p.smap.locate(id, s, l);
+  return p.sh.var[s] + (size_t)l * stride;
 }
 __device__ __forceinline__ float* ent_grad_row(const RelStepParams& p, int32_t id, int stride) {
-  if (p.shard_log2 == 0) return p.ent_grad + (size_t)id * stride;
-  return p.sh.grad[id & ((1 << p.shard_log2) - 1)] + (size_t)(id >> p.shard_log2) * stride;
+  if (!p.sharded) return p.ent_grad + (size_t)id * stride;
+  int s;
+  int32_t l;
+  p.smap.locate(id, s, l);
+  return p.sh.grad[s] + (size_t)l * stride;
 }
 __device__ __forceinline__ void ent_mark(const RelStepParams& p, int32_t id) {
-  if (p.shard_log2 == 0) {
+  if (!p.sharded) {
     mark_touched(p.ent_touched, id);
   } else {
-    mark_touched(p.sh.touched[id & ((1 << p.shard_log2) - 1)], id >> p.shard_log2);
+    int s;
+    int32_t l;
+    p.smap.locate(id, s, l);
+    mark_touched(p.sh.touched[s], l);
   }
 }
 

@@ -37,7 +37,8 @@ int sm_count() {
 // out[i, 0:dim] = l2_normalize(var[idx[i]]) -- one warp per row
 struct ExportShards {
   const float* var[MKE_MAX_SHARDS];
-  int log2g;  // 0: var[0] is the whole table
+  ShardMap map;
+  int sharded;  // 0: var[0] is the whole table
 };
 __global__ void table_export_kernel(ExportShards sh, int stride, int dim,
                                     int normalised, const int32_t* __restrict__ idx, int n,
@@ -46,7 +47,10 @@ __global__ void table_export_kernel(ExportShards sh, int stride, int dim,
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     const int row = idx ? __ldg(idx + i) : i;
-    const float* pv = sh.var[row & ((1 << sh.log2g) - 1)] + (size_t)(row >> sh.log2g) * stride;
+    int shard = 0;
+    int32_t local = row;
+    if (sh.sharded) sh.map.locate(row, shard, local);
+    const float* pv = sh.var[shard] + (size_t)local * stride;
     float ss = 0.f;
     for (int c = lane; c < dim; c += 32) {
       const float x = pv[c];
@@ -84,7 +88,8 @@ extern "C" int mke_table_export(const mke_table_t* table, const int32_t* idx_or_
   ExportShards sh{};
   sh.var[0] = table->var;
   if (table->n_shards > 1) {
-    sh.log2g = shard_log2(table->n_shards);
+    sh.sharded = 1;
+    sh.map = shard_map(table);
     for (int k = 0; k < table->n_shards; ++k) {
       MKE_CHECK_ARG(table->peer_var[k], "peer pointer %d is null", k);
       sh.var[k] = table->peer_var[k];

@@ -30,13 +30,25 @@ from .relation_view import clipped_slice, split_batch
 # ---------------------------------------------------------------------------------------------
 
 
-def shard_owner(ids, world):
+def shard_owner(ids, world, split=0):
+    """(owning rank, local row) of global row ids; split > 0 selects the KG-block placement
+    (mke_table_t.shard_split): KG1 = ids [0, split) on ranks [0, world/2), KG2 on the others."""
     ids = np.asarray(ids)
-    return ids % world, ids // world
+    if split <= 0:
+        return ids % world, ids // world
+    half = world // 2
+    second = ids >= split
+    x = np.where(second, ids - split, ids)
+    return np.where(second, half, 0) + x % half, x // half
 
 
-def local_rows(rows, rank, world):
-    return (rows - rank + world - 1) // world if rows > rank else 0
+def local_rows(rows, rank, world, split=0):
+    def part(n, r, g):
+        return (n - r + g - 1) // g if n > r else 0
+    if split <= 0:
+        return part(rows, rank, world)
+    half = world // 2
+    return part(split, rank, half) if rank < half else part(rows - split, rank - half, half)
 
 
 def rank_range(n, rank, world):
@@ -44,13 +56,22 @@ def rank_range(n, rank, world):
     return rank * n // world, (rank + 1) * n // world
 
 
-def rank_parts(n1, n2, global_batch, step, rank, world):
+def rank_parts(n1, n2, global_batch, step, rank, world, by_kg=False):
     """((start1, len1), (start2, len2), index_base): the pieces of the kg1 / kg2 triple lists that
-    `rank` trains in global step `step`, and the position of its first positive in the global batch."""
+    `rank` trains in global step `step`, and the position of its first positive in the global
+    batch (= its RNG coordinate base).  by_kg: ranks [0, world/2) share the kg1 slice and the others
+    the kg2 slice (goes with the KG-block placement: positives are trained where their rows live)."""
     b1, b2 = split_batch(n1, n2, global_batch)
     a1, e1 = clipped_slice(n1, b1, step)
     a2, e2 = clipped_slice(n2, b2, step)
     len1, len2 = e1 - a1, e2 - a2
+    if by_kg:
+        half = world // 2
+        if rank < half:
+            lo, hi = rank_range(len1, rank, half)
+            return (a1 + lo, hi - lo), (a2, 0), lo
+        lo, hi = rank_range(len2, rank - half, half)
+        return (a1 + len1, 0), (a2 + lo, hi - lo), len1 + lo
     lo, hi = rank_range(len1 + len2, rank, world)
     s1, t1 = min(lo, len1), min(hi, len1)
     s2, t2 = max(lo, len1) - len1, max(hi, len1) - len1
@@ -109,15 +130,16 @@ class PeerBuffer:
 class ShardedEmbeddingTable:
     """mke_table_t with n_shards = world: this rank's rows of a row-sharded normalised table."""
 
-    def __init__(self, rows, dim, normalised, group, init=None, name=""):
+    def __init__(self, rows, dim, normalised, group, init=None, name="", split=0):
         import torch.distributed as dist
         self.rows, self.dim, self.normalised, self.name = int(rows), int(dim), bool(normalised), name
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         assert self.world in (2, 4, 8), "row sharding supports 2, 4 or 8 ranks"
         self.stride = T.padded_stride(dim)
-        self.local_rows = local_rows(self.rows, self.rank, self.world)
+        self.split = int(split)
+        self.local_rows = local_rows(self.rows, self.rank, self.world, self.split)
         # every shard gets the same (maximal) allocation so that peer offsets never overrun
-        alloc_rows = local_rows(self.rows, 0, self.world)
+        alloc_rows = max(local_rows(self.rows, r, self.world, self.split) for r in range(self.world))
         self._bufs = [PeerBuffer((alloc_rows, self.stride), torch.float32, group),
                       PeerBuffer((alloc_rows, self.stride), torch.float32, group),
                       PeerBuffer((alloc_rows,), torch.uint8, group)]
@@ -125,18 +147,26 @@ class ShardedEmbeddingTable:
         self.device = self.var.device
         if init is not None:  # init is the GLOBAL [rows, dim] table; keep rows rank, rank + world, ...
             src = torch.as_tensor(np.asarray(init, dtype=np.float32)) if not torch.is_tensor(init) else init
-            mine = src[self.rank::self.world].to(self.device, torch.float32)
+            mine = src[torch.as_tensor(self.owned_ids())].to(self.device, torch.float32)
             self.var[: mine.shape[0], : self.dim] = mine
         self._slots = {}
         c = _cabi.MkeTable(var=self.var.data_ptr(), grad=self.grad.data_ptr(), touched=self.touched.data_ptr(),
                            rows=self.rows, stride=self.stride, dim=self.dim, normalised=int(self.normalised),
-                           grad_replicas=1, n_shards=self.world, shard_rank=self.rank)
+                           grad_replicas=1, n_shards=self.world, shard_rank=self.rank, shard_split=self.split)
         for k in range(self.world):
             c.peer_var[k], c.peer_grad[k], c.peer_touched[k] = (b.peers[k] for b in self._bufs)
         self._c = c
         self.grad_replicas = 1
         torch.cuda.synchronize()
         dist.barrier(group)
+
+    def owned_ids(self):
+        """global ids of this rank's rows, in local-row order"""
+        ids = np.arange(self.rows)
+        owner, local = shard_owner(ids, self.world, self.split)
+        mine = ids[owner == self.rank]
+        assert np.array_equal(local[owner == self.rank], np.arange(mine.size))
+        return mine
 
     @property
     def c(self):
@@ -181,7 +211,7 @@ class ShardedRelationView:
     SLOT = "relation"
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size, neg_num, lr, seed, group,
-                 ent_init=None, rel_init=None, filter1=None, filter2=None, rel_replicas=1):
+                 ent_init=None, rel_init=None, filter1=None, filter2=None, rel_replicas=1, by_kg=True):
         import torch.distributed as dist
         self._lib = _cabi.load()
         self.group = group
@@ -190,7 +220,11 @@ class ShardedRelationView:
         self.dim, self.K, self.lr, self.seed = int(dim), int(neg_num), float(lr), int(seed)
         self.batch_size = int(batch_size)              # per rank
         self.global_batch = self.batch_size * self.world
-        self.ent = ShardedEmbeddingTable(n_ent, dim, True, group, init=ent_init, name="rv_ent_embeds")
+        # by_kg: KG-block placement + positives trained on the ranks of their own KG (kg1 ids are
+        # [0, ent_split), kg2 ids [ent_split, n_ent)); otherwise plain id % G placement
+        self.by_kg = bool(by_kg)
+        self.ent = ShardedEmbeddingTable(n_ent, dim, True, group, init=ent_init, name="rv_ent_embeds",
+                                         split=ent_split if self.by_kg else 0)
         self.rel = T.EmbeddingTable(n_rel, dim, True, self.device, init=rel_init, name="rel_embeds", flags=False,
                                     grad_replicas=rel_replicas)
         t1 = np.ascontiguousarray(triples1, dtype=np.int32).reshape(-1, 3)
@@ -202,7 +236,10 @@ class ShardedRelationView:
         self.kg1 = T.KGSampler(entity_base=0, n_entities=ent_split, triple_set=self.set1, device=self.device)
         self.kg2 = T.KGSampler(entity_base=ent_split, n_entities=n_ent - ent_split, triple_set=self.set2,
                                device=self.device)
-        cap = self.batch_size + 1
+        # most positives one rank can get in a step (by_kg: a KG's share of the global batch over
+        # half of the ranks, which exceeds batch_size for the larger KG)
+        b1, b2 = split_batch(self.n1, self.n2, self.global_batch)
+        cap = (max(b1, b2) // max(self.world // 2, 1) + 2) if self.by_kg else self.batch_size + 2
         self._neg_ent = torch.empty(cap * max(self.K, 1), dtype=torch.int32, device=self.device)
         self._neg_side = torch.empty(cap, dtype=torch.int32, device=self.device)
         self.loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -217,7 +254,8 @@ class ShardedRelationView:
     def step(self, step_in_epoch):
         """one global step; returns the number of positives this rank trained"""
         import torch.distributed as dist
-        (a1, l1), (a2, l2), base = rank_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank, self.world)
+        (a1, l1), (a2, l2), base = rank_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank, self.world,
+                                               by_kg=self.by_kg)
         stream = _cabi.current_stream()
         p1 = self.triples1.data_ptr() + 12 * a1
         p2 = self.triples2.data_ptr() + 12 * a2

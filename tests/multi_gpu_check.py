@@ -28,9 +28,10 @@ def main():
     dim, K, B, lr, seed = 75, 10, 3000, 0.001, 21
     ent0 = T.xavier_truncated_normal(kgs["n_ent"], dim, gen)
     rel0 = T.xavier_truncated_normal(kgs["n_rel"], dim, gen)
+    by_kg = os.environ.get("MKE_BY_KG", "1") == "1"
     sv = ShardedRelationView(kgs["n_ent"], kgs["n_rel"], dim, kgs["triples1"], kgs["triples2"], kgs["ent_split"],
                              batch_size=B, neg_num=K, lr=lr, seed=seed, group=dist.group.WORLD, ent_init=ent0,
-                             rel_init=rel0)
+                             rel_init=rel0, by_kg=by_kg)
     steps = 5
     sv.loss_acc.zero_()
     trained = sum(sv.step(s) for s in range(steps))
@@ -45,7 +46,7 @@ def main():
     torch.cuda.synchronize()
     ok = True
     mine = sv.ent.raw_local()
-    want = rv.ent.raw()[rank::world]
+    want = rv.ent.raw()[sv.ent.owned_ids()]
     d_ent = float(np.abs(mine - want).max())
     d_rel = float(np.abs(sv.rel.raw() - rv.rel.raw()).max())
     d_exp = float(np.abs(sv.ent.eval(idx=np.arange(0, kgs["n_ent"], 97)) - rv.ent.eval(idx=np.arange(0, kgs["n_ent"], 97))).max())
@@ -59,7 +60,7 @@ def main():
     print("rank %d: d_ent %.2e d_rel %.2e d_export %.2e moved %.2e loss %.6f vs %.6f trained %d vs %d" % (
         rank, d_ent, d_rel, d_exp, moved, float(tot[0]), ref_loss, int(tot[1]), ref_trained), flush=True)
     if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if float(flags) == 1.0 else "FAIL", "world", world, flush=True)
+        print("MULTI_GPU_CHECK", "PASS" if float(flags) == 1.0 else "FAIL", "world", world, "by_kg", by_kg, flush=True)
     sv.close()
     dist.destroy_process_group()
     return 0 if float(flags) == 1.0 else 1

@@ -43,7 +43,7 @@ def test_bad_arguments_are_reported_not_thrown():
 
 
 def test_struct_layout_matches_header():
-    # mke_table_t: 3 pointers + 7 int32 (+4 pad) + 3 x 8 peer pointers; mke_tripleset_t; mke_kg_sampler_t
-    assert ctypes.sizeof(_cabi.MkeTable) == 3 * 8 + 7 * 4 + 4 + 3 * 8 * 8
+    # mke_table_t: 3 pointers + 9 int32 (+4 pad) + 3 x 8 peer pointers; mke_tripleset_t; mke_kg_sampler_t
+    assert ctypes.sizeof(_cabi.MkeTable) == 3 * 8 + 9 * 4 + 4 + 3 * 8 * 8
     assert ctypes.sizeof(_cabi.MkeTripleSet) == 16
     assert ctypes.sizeof(_cabi.MkeKgSampler) == 8 + 4 + 4 + 8 + 4 + 4 + 16

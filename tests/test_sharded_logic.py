@@ -25,13 +25,15 @@ def test_rank_parts_partition_the_global_batch():
             a1, e1 = clipped_slice(n1, b1, step)
             a2, e2 = clipped_slice(n2, b2, step)
             want = [("1", i) for i in range(a1, e1)] + [("2", i) for i in range(a2, e2)]
-            got, base_expected = [], 0
-            for rank in range(world):
-                (s1, l1), (s2, l2), base = rank_parts(n1, n2, gb, step, rank, world)
-                assert base == base_expected and l1 >= 0 and l2 >= 0
-                got += [("1", i) for i in range(s1, s1 + l1)] + [("2", i) for i in range(s2, s2 + l2)]
-                base_expected += l1 + l2
-            assert got == want
+            for by_kg in (False, True):
+                got, base_expected = [], 0
+                for rank in range(world):
+                    (s1, l1), (s2, l2), base = rank_parts(n1, n2, gb, step, rank, world, by_kg=by_kg)
+                    assert base == base_expected and l1 >= 0 and l2 >= 0
+                    assert not by_kg or (l2 == 0 if rank < world // 2 else l1 == 0)
+                    got += [("1", i) for i in range(s1, s1 + l1)] + [("2", i) for i in range(s2, s2 + l2)]
+                    base_expected += l1 + l2
+                assert got == want
     ids = np.arange(23)
     for world in (2, 4, 8):
         owner, local = shard_owner(ids, world)
@@ -39,6 +41,14 @@ def test_rank_parts_partition_the_global_batch():
         assert sum(local_rows(23, r, world) for r in range(world)) == 23
         for r in range(world):
             assert local_rows(23, r, world) == int((owner == r).sum())
+        # KG-block placement: KG1 = ids [0, 9) on the first half of the ranks, KG2 on the second
+        owner, local = shard_owner(ids, world, split=9)
+        half = world // 2
+        assert (owner[:9] < half).all() and (owner[9:] >= half).all()
+        for r in range(world):
+            mine = ids[owner == r]
+            assert local_rows(23, r, world, split=9) == mine.size
+            assert np.array_equal(local[owner == r], np.arange(mine.size))  # local rows are dense, in id order
 
 
 def _free_port():
@@ -68,7 +78,8 @@ def _worker(rank, world, port, golden_path, out):
     ent, rel = orv.DenseTable(ent0, True, torch.float64), orv.DenseTable(rel0, True, torch.float64)
     K, per_rank, seed = 5, 60, 9
     for step in range(3):
-        (a1, l1), (a2, l2), base = rank_parts(len(t1), len(t2), per_rank * world, step, rank, world)
+        (a1, l1), (a2, l2), base = rank_parts(len(t1), len(t2), per_rank * world, step, rank, world,
+                                              by_kg=(step % 2 == 1))
         p1, p2 = t1[a1:a1 + l1], t2[a2:a2 + l2]
         skey = ds.stream_key(seed, step)
         neg = []
