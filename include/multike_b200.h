@@ -204,6 +204,18 @@ int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
                                 const mke_table_t* b, float* acc_b, float lr_b, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ITC cross-view alignment step (MultiKE_model.py:225-239 + losses.py:66-69), fused:
+ *   loss += scale * sum_i ( name_weight |F_i - N_i|^2 + |F_i - R_i|^2 + |F_i - A_i|^2 ),  i = idx[.]
+ * F = ent_embeds, N = name_embeds (constant: grad NULL), R = rv_ent_embeds, A = av_ent_embeds, each
+ * read through its normalised view; gradients are accumulated into the trainable tables (phase 2:
+ * mke_rows_apply_adagrad with args.ITC_learning_rate and this graph's accumulator slots).
+ * scale = args.cv_weight, name_weight = args.cv_name_weight.
+ * ------------------------------------------------------------------------------------------ */
+int mke_align_fwd_bwd(const mke_table_t* shared, const mke_table_t* name, const mke_table_t* rv,
+                      const mke_table_t* av, const int32_t* idx, int32_t n, float name_weight,
+                      float scale, double* loss_accum, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * losses.py as free functions on already gathered [n, dim] matrices (row stride ld floats).
  * ------------------------------------------------------------------------------------------ */
 
@@ -316,6 +328,19 @@ int mke_sample_structured_at(const int32_t* pos1, int32_t len1, const mke_kg_sam
                              const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
                              int32_t K, uint64_t seed, uint64_t step, int32_t index_base,
                              int32_t* neg_ent, uint32_t* neg_side, mke_stream_t stream);
+
+/*
+ * Attribute-view negatives (attr_batch.py:13-25 generate_neg_attribute_triples): for every positive
+ * (h, a, v) K corrupted HEADS, each drawn from the candidate pool of h (neighbour list or the KG's
+ * entity list) and redrawn while (h', a, v) is a known attribute triple of that KG (kgX->set built
+ * over (h, a, v) rows); independent draws, i.e. with replacement, as random.choice does.
+ * neg_head [(len1+len2) * K], positive-major.  The reference retries without bound; try 63 is
+ * accepted unfiltered.  pos rows are (h, a, v) int32; weights ride along on the caller's side.
+ */
+int mke_sample_attribute_heads(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                               const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                               int32_t K, uint64_t seed, uint64_t step, int32_t index_base,
+                               int32_t* neg_head, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Peer memory for row-sharded tables (one process per GPU; handles travel over torch.distributed).

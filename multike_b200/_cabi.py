@@ -87,6 +87,7 @@ SIGNATURES = {
     "mke_rel_step_structured": (_i32, [_PT, _PT, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rel_step_structured2": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
+    "mke_align_fwd_bwd": (_i32, [_PT, _PT, _PT, _PT, _vp, _i32, _f32, _f32, _vp, _vp]),
     "mke_dense_logistic_fwd_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mke_dense_sqdist_fwd_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mke_timing_enable": (_i32, [_i32]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     "mke_sample_uniform": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp]),
     "mke_sample_structured": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _vp, _vp, _vp]),
     "mke_sample_structured_at": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _i32, _vp, _vp, _vp]),
+    "mke_sample_attribute_heads": (_i32, [_vp, _i32, _PK, _vp, _i32, _PK, _i32, _u64, _u64, _i32, _vp, _vp]),
     "mke_peer_alloc": (_i32, [_u64, _c.POINTER(_c.c_void_p)]),
     "mke_peer_free": (_i32, [_vp]),
     "mke_ipc_export": (_i32, [_vp, _c.c_char_p]),

@@ -108,6 +108,33 @@ static int launch_sample(const int32_t* pos1, int32_t len1, const mke_kg_sampler
   return 0;
 }
 
+// attr_batch.py:13-25 generate_neg_attribute_triples: head-only corruption, K independent draws per
+// positive (WITH replacement across the K), each redrawn until (h', a, v) is not a known attribute
+// triple.  The reference retries without bound; here try kAttrMaxTry - 1 is accepted unfiltered.
+constexpr uint32_t kAttrMaxTry = 64;
+__global__ void attr_sample_kernel(const int32_t* __restrict__ pos1, int len1, mke_kg_sampler_t kg1,
+                                   const int32_t* __restrict__ pos2, int len2, mke_kg_sampler_t kg2, int K,
+                                   uint64_t skey, int index_base, int32_t* __restrict__ neg_head) {
+  const long long total = (long long)(len1 + len2) * K;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(g / K), j = (int)(g % K);
+    const bool first = i < len1;
+    const int32_t* row = first ? pos1 + 3 * (size_t)i : pos2 + 3 * (size_t)(i - len1);
+    const int32_t h = __ldg(row), a = __ldg(row + 1), v = __ldg(row + 2);
+    const KgView kg = kg_view(kg1, kg2, first);
+    const CandPool pool = kg.pool(h);
+    int32_t e = h;
+    for (uint32_t tr = 0; tr < kAttrMaxTry; ++tr) {
+      // coordinates: (positive, try, draw) -- try fits the 4-bit field only up to 15, so the try
+      // index is folded into the draw field instead: draw = j + 32 * try  (j < 32, try < 64)
+      e = pool.at(draw_index(draw64(skey, (uint32_t)(index_base + i), 0u, (uint32_t)j + 32u * tr), pool.n));
+      if (tr == kAttrMaxTry - 1 || !tripleset_contains(kg.set, triple_key(e, a, v))) break;
+    }
+    neg_head[g] = e;
+  }
+}
+
 static int check_set(const mke_tripleset_t* set) {
   MKE_CHECK_ARG(set && set->slots, "null triple set");
   MKE_CHECK_ARG(set->capacity >= 8 && (set->capacity & (set->capacity - 1)) == 0,
@@ -167,4 +194,34 @@ extern "C" int mke_sample_structured_at(const int32_t* pos1, int32_t len1, const
   MKE_CHECK_ARG((neg_ent && neg_side) || len1 + len2 == 0, "neg_ent/neg_side are null");
   return launch_sample(pos1, len1, kg1, pos2, len2, kg2, K, seed, step, index_base, nullptr, neg_ent, neg_side,
                        (cudaStream_t)stream);
+}
+
+extern "C" int mke_sample_attribute_heads(const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,
+                                          const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
+                                          int32_t K, uint64_t seed, uint64_t step, int32_t index_base,
+                                          int32_t* neg_head, mke_stream_t stream) {
+  MKE_CHECK_ARG(K >= 1 && K <= MKE_MAX_NEG, "K=%d outside [1,%d]", K, MKE_MAX_NEG);
+  MKE_CHECK_ARG(len1 >= 0 && len2 >= 0 && index_base >= 0, "bad batch length / index_base");
+  MKE_CHECK_ARG(len1 == 0 || (pos1 && kg1), "kg1 slice needs positives and a sampler");
+  MKE_CHECK_ARG(len2 == 0 || (pos2 && kg2), "kg2 slice needs positives and a sampler");
+  const long long total = (long long)(len1 + len2) * K;
+  if (total == 0) return 0;
+  MKE_CHECK_ARG(neg_head, "neg_head is null");
+  mke_kg_sampler_t a{}, b{};
+  if (kg1) a = *kg1;
+  if (kg2) b = *kg2;
+  for (const mke_kg_sampler_t* kg : {len1 ? kg1 : nullptr, len2 ? kg2 : nullptr}) {
+    if (!kg) continue;
+    MKE_CHECK_ARG(kg->n_entities >= 1, "empty candidate pool");
+    MKE_CHECK_ARG(!kg->set.slots || (kg->set.capacity >= 8 && (kg->set.capacity & (kg->set.capacity - 1)) == 0),
+                  "triple-set capacity must be a power of two >= 8");
+  }
+  long long blocks = (total + 255) / 256;
+  const long long full = (long long)sm_count() * 16;
+  if (blocks > full) blocks = full;
+  attr_sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pos1, len1, a, pos2, len2, b, K,
+                                                                         stream_key(seed, step), index_base,
+                                                                         neg_head);
+  MKE_CHECK_LAUNCH("attr_sample_kernel");
+  return 0;
 }

@@ -283,3 +283,26 @@ def sample_structured(pos1, kg1, pos2, kg2, K, seed, step, device="cuda"):
                                           int(K), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
                                           ne.data_ptr(), ns.data_ptr(), _cabi.current_stream()))
     return ne, ns
+
+
+def sample_attribute_heads(pos1, kg1, pos2, kg2, K, seed, step, index_base=0, device="cuda"):
+    """mke_sample_attribute_heads: corrupted heads [(len1+len2), K] for (h, a, v) positives."""
+    lib = _cabi.load()
+    pos1, pos2 = _i32(pos1, device), _i32(pos2, device)
+    len1 = 0 if pos1 is None else pos1.numel() // 3
+    len2 = 0 if pos2 is None else pos2.numel() // 3
+    out = torch.empty(len1 + len2, K, dtype=torch.int32, device=device)
+    _cabi.check(lib.mke_sample_attribute_heads(_cabi.ptr(pos1), len1, kg1.c if kg1 is not None else None,
+                                               _cabi.ptr(pos2), len2, kg2.c if kg2 is not None else None, int(K),
+                                               int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1), int(index_base),
+                                               out.data_ptr(), _cabi.current_stream()))
+    return out
+
+
+def align_fwd_bwd(shared, name, rv, av, idx, loss_accum, name_weight=1.0, scale=1.0):
+    """mke_align_fwd_bwd: ITC cross-view alignment term + backward for a batch of entity ids."""
+    lib = _cabi.load()
+    idx = _i32(idx, shared.device)
+    _cabi.check(lib.mke_align_fwd_bwd(shared.c, name.c, rv.c, av.c, idx.data_ptr(), idx.numel(), float(name_weight),
+                                      float(scale), _cabi.ptr(loss_accum), _cabi.current_stream()))
+    return idx

@@ -95,3 +95,28 @@ def sample_batch(pos1, kg1, pos2, kg2, K, seed, step):
     for k, (h, r, t) in enumerate(pos2):
         out += sample_one(kg2, int(h), int(r), int(t), K, skey, len(pos1) + k)
     return np.asarray(out, dtype=np.int32).reshape(-1, 3)
+
+
+ATTR_MAX_TRY = 64
+
+
+def sample_attribute_heads(pos1, kg1, pos2, kg2, K, seed, step, index_base=0):
+    """mke_sample_attribute_heads: restatement of attr_batch.py:13-25 with the counter-based RNG
+    (draw coordinate = j + 32 * try); returns int32 [(n1+n2), K] corrupted heads."""
+    skey = stream_key(seed, step)
+    pos1 = np.asarray(pos1, dtype=np.int64).reshape(-1, 3)
+    pos2 = np.asarray(pos2, dtype=np.int64).reshape(-1, 3)
+    out = []
+    for i, (h, a, v) in enumerate(np.concatenate([pos1, pos2])):
+        kg = kg1 if i < len(pos1) else kg2
+        at, n = kg.pool(int(h))
+        row = []
+        for j in range(K):
+            e = int(h)
+            for tr in range(ATTR_MAX_TRY):
+                e = at(draw_index(draw64(skey, index_base + i, 0, j + 32 * tr), n))
+                if tr == ATTR_MAX_TRY - 1 or not kg.contains(e, int(a), int(v)):
+                    break
+            row.append(e)
+        out.append(row)
+    return np.asarray(out, dtype=np.int32).reshape(-1, K)

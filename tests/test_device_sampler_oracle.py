@@ -97,3 +97,33 @@ def test_neighbour_lists_restrict_candidates(golden):
                 assert nh in nb[h]
             if nt != t and t % 2 == 0:
                 assert nt in nb[t]
+
+
+def test_attribute_head_sampler_semantics_match_reference(golden):
+    """oracle restatement of the device attribute sampler keeps attr_batch.py:13-25: head-only,
+    K independent draws from the KG's entities, never a known (h, a, v)."""
+    g = golden("ref_batch_attribute.npz")
+    a1 = g["a1"]
+    trip = a1[:, :3].astype(np.int64)
+    n_ent = 40
+    kg = ds.KG(entity_base=0, n_entities=n_ent, triples=trip)
+    K = 4
+    neg = ds.sample_attribute_heads(trip[:120], kg, np.zeros((0, 3)), kg, K, seed=2, step=1)
+    known = {tuple(int(x) for x in t) for t in trip}
+    assert neg.shape == (120, K) and neg.min() >= 0 and neg.max() < n_ent
+    for (h, a, v), row in zip(trip[:120], neg):
+        for e in row:
+            assert (int(e), int(a), int(v)) not in known
+    # reference restatement under its own RNG: same support and a flat histogram for both
+    random.seed(4)
+    ents = list(range(n_ent))
+    pos = [(int(h), int(a), int(v), 1.0) for h, a, v in trip[:120]]
+    ref = ref_batch.neg_attribute_triples(pos, {(h, a, v, 1.0) for h, a, v in known}, ents, K)
+    ref_heads = np.array([t[0] for t in ref])
+    assert len(ref) == 120 * K and all(t[1:3] == p[1:3] for t, p in zip(ref, [p for p in pos for _ in range(K)]))
+    hr, hd = np.bincount(ref_heads, minlength=n_ent), np.bincount(neg.ravel(), minlength=n_ent)
+    expect = 120 * K / n_ent
+    assert np.abs(hr - expect).max() < 6 * np.sqrt(expect) and np.abs(hd - expect).max() < 6 * np.sqrt(expect)
+    # index_base shifts the RNG coordinates: a rank holding positions [60, 120) draws the same
+    part = ds.sample_attribute_heads(trip[60:120], kg, np.zeros((0, 3)), kg, K, seed=2, step=1, index_base=60)
+    assert np.array_equal(part, neg[60:])

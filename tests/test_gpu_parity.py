@@ -517,3 +517,88 @@ def test_bad_arguments_on_device(G):
     with pytest.raises(_cabi.MkeError):
         T.rel_step_structured(ent, rel, np.zeros((1, 3), np.int32), np.zeros((1, 40), np.int32),
                               np.zeros(1, np.uint32), 40, T.new_loss_accumulator())
+
+
+def test_attribute_sampler_bit_exact_and_transe_step(G, golden):
+    """mke_sample_attribute_heads == its CPU restatement (index work: exact), then the
+    attribute-view TransE step of losses.py:15-27 on those negatives == the torch oracle."""
+    U, T = G
+    from oracle import losses as ol
+    from oracle.tf_semantics import l2_normalize
+    g = golden("ref_batch_attribute.npz")
+    a1, a2 = g["a1"], g["a2"]
+    t1, t2 = a1[:, :3].astype(np.int32), a2[:, :3].astype(np.int32)
+    w1, w2 = a1[:, 3], a2[:, 3]
+    n_ent, K = 40, 3
+    dk1 = T.KGSampler(entity_base=0, n_entities=n_ent, triple_set=T.TripleSet(t1))
+    dk2 = T.KGSampler(entity_base=n_ent, n_entities=n_ent, triple_set=T.TripleSet(t2))
+    ok1 = ds.KG(entity_base=0, n_entities=n_ent, triples=t1)
+    ok2 = ds.KG(entity_base=n_ent, n_entities=n_ent, triples=t2)
+    p1, p2 = t1[10:90], t2[5:70]
+    got = T.sample_attribute_heads(p1, dk1, p2, dk2, K, 8, 2).cpu().numpy()
+    want = ds.sample_attribute_heads(p1, ok1, p2, ok2, K, 8, 2)
+    assert np.array_equal(got, want)
+    got_b = T.sample_attribute_heads(p1[40:], dk1, p2, dk2, K, 8, 2, index_base=40).cpu().numpy()
+    assert np.array_equal(got_b, want[40:])
+    # the step: positives weighted, negatives = (h', a, v) with the positive's weight
+    rng = np.random.default_rng(0)
+    n_attr, n_val, d = 8, int(max(t1[:, 2].max(), t2[:, 2].max())) + 1, 75
+    ent0, att0, val0 = rng.normal(0, 0.02, (2 * n_ent, d)), rng.normal(0, 0.02, (n_attr, d)), rng.normal(0, 0.3, (n_val, d))
+    ent = T.EmbeddingTable(2 * n_ent, d, True, "cuda", init=ent0, flags=True, grad_replicas=1)
+    att = T.EmbeddingTable(n_attr, d, False, "cuda", init=att0)
+    val = T.EmbeddingTable(n_val, d, False, "cuda", init=val0, trainable=False)
+    pos = np.concatenate([p1, p2])
+    pw = np.concatenate([w1[10:90], w2[5:70]])
+    nh = want.reshape(-1)
+    na, nv, nw = np.repeat(pos[:, 1], K), np.repeat(pos[:, 2], K), np.repeat(pw, K)
+    acc = T.new_loss_accumulator()
+    T.triple_fwd_bwd(ent, att, val, pos[:, 0], pos[:, 1], pos[:, 2], acc, w=pw)
+    T.triple_fwd_bwd(ent, att, val, nh, na, nv, acc, w=nw, negative=True)
+    Ve, Va, Vv = torch.tensor(ent0, requires_grad=True), torch.tensor(att0, requires_grad=True), torch.tensor(val0)
+    E = l2_normalize(Ve, 1)
+    loss = ol.attribute_logistic_loss(E[pos[:, 0]], Va[pos[:, 1]], Vv[pos[:, 2]], torch.tensor(pw), E[nh], Va[na], Vv[nv],
+                                      torch.tensor(nw))
+    ge, ga = torch.autograd.grad(loss, [Ve, Va])
+    assert U.loss_value(acc) == pytest.approx(float(loss), rel=LOSS_RTOL)
+    ent.apply_adagrad("attribute", 0.001)
+    att.apply_adagrad("attribute", 0.001)
+    want_e = ent0 - 0.001 * ge.numpy() / np.sqrt(0.1 + ge.numpy() ** 2)
+    want_a = att0 - 0.001 * ga.numpy() / np.sqrt(0.1 + ga.numpy() ** 2)
+    np.testing.assert_allclose(ent.raw(), want_e, rtol=0, atol=ROW_ATOL)
+    np.testing.assert_allclose(att.raw(), want_a, rtol=0, atol=ROW_ATOL)
+
+
+def test_itc_alignment_step_matches_oracle(G):
+    """mke_align_fwd_bwd (MultiKE_model.py:225-239): cv_weight * (cv_name_weight |F-N|^2 + |F-R|^2 +
+    |F-A|^2) over one index vector, three normalised trainable tables + the constant name table,
+    Adagrad with its own slots and the ITC learning rate."""
+    U, T = G
+    from oracle import losses as ol
+    from oracle.tf_semantics import l2_normalize
+    rng = np.random.default_rng(5)
+    n, d, B = 500, 75, 128
+    F0, R0, A0 = (rng.normal(0, 0.02, (n, d)) for _ in range(3))
+    N0 = rng.normal(0, 0.1, (n, d))
+    tabs = [T.EmbeddingTable(n, d, True, "cuda", init=x, flags=True, grad_replicas=1) for x in (F0, R0, A0)]
+    name = T.EmbeddingTable(n, d, False, "cuda", init=N0, trainable=False)
+    idx = rng.choice(n, B, replace=False)  # random.sample(entities, batch_size): distinct ids
+    cv_weight, cv_name_weight, lr = 1.0, 1.0, 0.004
+    for cv_weight, cv_name_weight in [(1.0, 1.0), (0.7, 2.5)]:
+        acc = T.new_loss_accumulator()
+        T.align_fwd_bwd(tabs[0], name, tabs[1], tabs[2], idx, acc, name_weight=cv_name_weight, scale=cv_weight)
+        before = [t.raw().astype(np.float64) for t in tabs]
+        V = [torch.tensor(b, requires_grad=True) for b in before]
+        Fv, Rv, Av = (l2_normalize(v, 1)[idx] for v in V)
+        inner = cv_name_weight * ol.alignment_loss(Fv, torch.tensor(N0)[idx]) + ol.alignment_loss(Fv, Rv) + \
+            ol.alignment_loss(Fv, Av)
+        grads = torch.autograd.grad(cv_weight * inner, V)
+        assert U.loss_value(acc) == pytest.approx(float(cv_weight * inner), rel=LOSS_RTOL)
+        for t, b, gv in zip(tabs, before, grads):
+            slot = t.adagrad_slot("cross_name")
+            a0 = slot[:, :d].double().cpu().numpy().copy()
+            t.apply_adagrad("cross_name", lr)
+            a1 = a0 + gv.numpy() ** 2
+            np.testing.assert_allclose(t.raw(), b - lr * gv.numpy() / np.sqrt(a1), rtol=0, atol=ROW_ATOL)
+            untouched = np.ones(n, bool)
+            untouched[idx] = False
+            assert np.array_equal(t.raw()[untouched], b[untouched].astype(np.float32))
