@@ -1,6 +1,7 @@
 // Step / epoch driver: the inner loop of MultiKE.train_relation_view_1epo
 // (MultiKE_model.py:302-313) as a sequence of kernel launches on two streams, issued from C so
 // that a step costs no interpreter time.  Batching follows base/batch.py:33-54.
+#include <cstdlib>
 #include <utility>
 #include <vector>
 #include "mke_common.cuh"
@@ -69,6 +70,24 @@ extern "C" int mke_rel_train_steps(const mke_rel_view_t* v, int32_t first_step, 
   const bool ahead = v->K > 0 && v->neg_ent[0] && v->neg_ent[1] && v->neg_side[0] && v->neg_side[1] &&
                      side_ != nullptr && side_ != main_;
   cudaStream_t main = (cudaStream_t)main_, side = ahead ? (cudaStream_t)side_ : (cudaStream_t)main_;
+  // Experiment knob (MKE_L2_PERSIST=<MB>): pin the entity gradient table in L2 -- phase 1 reduces
+  // into it and phase 2 reads and re-zeroes it, so it need not travel to HBM in between.
+  static const int l2_mb = getenv("MKE_L2_PERSIST") ? atoi(getenv("MKE_L2_PERSIST")) : 0;
+  if (l2_mb > 0) {
+    static bool limit_set = false;
+    if (!limit_set) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_mb << 20);
+      limit_set = true;
+    }
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = v->ent->grad;
+    attr.accessPolicyWindow.num_bytes = (size_t)table_local_rows(v->ent) * v->ent->stride * sizeof(float);
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute((cudaStream_t)main_, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+  }
   const int steps_per_epoch = (int)(((long long)v->n1 + v->n2 + v->batch_size - 1) / v->batch_size);
   int dev = 0;
   cudaGetDevice(&dev);

@@ -6,9 +6,9 @@ device tables and the kernels behind the C-ABI (multike_b200/relation_view.py). 
 purpose: batches and negatives never leave the device (``steps_tasks`` / ``batch_queue`` are
 accepted and ignored), and the per-epoch print lines are kept verbatim.
 
+Also mirrored: ITC common-space learning (:225-239, :458-473) on the fused alignment kernel.
 Not mirrored yet (SURVEY.md section 8 "next" rows; calling them raises NotImplementedError): the
-attribute-view CNN graphs (MultiKE_model.py:134-151, 172-185, 203-221), common-space learning
-(:225-239) and space mapping (:241-261).
+attribute-view CNN graphs (MultiKE_model.py:134-151, 172-185, 203-221) and space mapping (:241-261).
 """
 import math
 import os
@@ -82,10 +82,12 @@ class MultiKE:
             len(value_vectors), dim, False, dev, init=np.asarray(value_vectors, np.float32), trainable=False)
         self.name_embeds = None if name_vectors is None else T.EmbeddingTable(
             len(name_vectors), dim, False, dev, init=np.asarray(name_vectors, np.float32), trainable=False)
-        self.av_ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["av_ent_embeds"])
+        self.av_ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["av_ent_embeds"], flags=True,
+                                              grad_replicas=1)
         # False important! (MultiKE_model.py:96-97)
         self.attr_embeds = T.EmbeddingTable(max(n_attr, 1), dim, False, dev, init=self._init["attr_embeds"])
-        self.ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["ent_embeds"])
+        self.ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["ent_embeds"], flags=True,
+                                           grad_replicas=1)
         self.rv_ent_embeds = None  # created with the relation-view graph (they own the triple lists)
         self.rel_embeds = None
 
@@ -123,16 +125,44 @@ class MultiKE:
         raise NotImplementedError("attribute-view CNN / common-space / space-mapping graphs are SURVEY.md "
                                   "section 8 'next' rows; not part of the relation-view hot path")
 
+    def _define_common_space_learning_graph(self):
+        """MultiKE_model.py:225-239: cv_weight * (cv_name_weight |F-N|^2 + |F-R|^2 + |F-A|^2), Adagrad
+        with args.ITC_learning_rate and its own accumulator slots"""
+        assert self.name_embeds is not None, "the common-space graph needs data.local_name_vectors"
+        self._cn_slot = "cross_name"
+
     _define_attribute_view_graph = _not_yet
     _define_cross_kg_entity_reference_attribute_view_graph = _not_yet
     _define_cross_kg_attribute_reference_graph = _not_yet
-    _define_common_space_learning_graph = _not_yet
     _define_space_mapping_graph = _not_yet
     train_attribute_view_1epo = _not_yet
     train_cross_kg_entity_inference_attribute_view_1epo = _not_yet
     train_cross_kg_attribute_inference_1epo = _not_yet
     train_shared_space_mapping_1epo = _not_yet
-    train_common_space_learning_1epo = _not_yet
+
+    def train_common_space_learning_1epo(self, epoch, entities):
+        """MultiKE_model.py:458-473"""
+        start = time.time()
+        ents = torch.as_tensor(np.asarray(entities, dtype=np.int32)).to(self.device)
+        n = ents.numel()
+        steps = int(math.ceil(n / self.args.entity_batch_size))
+        batch_size = self.args.entity_batch_size if steps > 1 else n
+        acc = T.new_loss_accumulator(self.device)
+        lr, cvw = self.args.ITC_learning_rate, float(self.args.cv_weight)
+        tabs = (self.ent_embeds, self._rv.ent, self.av_ent_embeds)
+        trained = 0
+        for _ in range(steps):
+            pick = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()  # random.sample
+            T.align_fwd_bwd(self.ent_embeds, self.name_embeds, self._rv.ent, self.av_ent_embeds, pick, acc,
+                            name_weight=self.args.cv_name_weight, scale=cvw)
+            for t in tabs:
+                t.apply_adagrad(self._cn_slot, lr)
+            trained += batch_size
+        # the fetched cross_name_loss is the un-weighted sum (the optimizer minimises cv_weight * loss)
+        epoch_loss = float(acc.item()) / (cvw if cvw != 0 else 1.0) / max(trained, 1)
+        print('epoch {} of common space learning, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss,
+                                                                                           time.time() - start))
+        return epoch_loss
 
     # --- reads (MultiKE_model.py:263-287) ------------------------------------------------------
     def eval_kg1_ent_embeddings(self):

@@ -120,3 +120,63 @@ def sample_attribute_heads(pos1, kg1, pos2, kg2, K, seed, step, index_base=0):
             row.append(e)
         out.append(row)
     return np.asarray(out, dtype=np.int32).reshape(-1, K)
+
+
+# ---- vectorised front end (numpy) for full-size CPU runs; same results as sample_batch -------------
+def _mix64_np(x):
+    x = x.astype(np.uint64)
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def _draw64_np(skey, i, tr, c):
+    coord = (i.astype(np.uint64) << np.uint64(20)) | (np.uint64(tr) << np.uint64(16)) | c.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        return _mix64_np(np.uint64(skey) + (coord + np.uint64(1)) * np.uint64(GAMMA))
+
+
+def sample_batch_fast(pos1, kg1, pos2, kg2, K, seed, step, index_base=0):
+    """sample_batch for uniform pools (no neighbour lists), vectorised: round 0 is evaluated for all
+    positives at once; positives whose round-0 candidates repeat an entity or hit a known triple
+    are replayed through sample_one (the sequential definition)."""
+    skey = stream_key(seed, step)
+    pos1 = np.asarray(pos1, dtype=np.int64).reshape(-1, 3)
+    pos2 = np.asarray(pos2, dtype=np.int64).reshape(-1, 3)
+    out = np.empty(((len(pos1) + len(pos2)) * K, 3), dtype=np.int32)
+    off = 0
+    for pos, kg in ((pos1, kg1), (pos2, kg2)):
+        n = len(pos)
+        if n == 0:
+            continue
+        assert kg.neighbours is None and kg.entity_list is None
+        i = np.arange(off, off + n, dtype=np.uint64) + np.uint64(index_base)
+        with np.errstate(over="ignore"):
+            head_side = (_draw64_np(skey, i, 0, np.full(n, SIDE_DRAW, dtype=np.uint64)) >> np.uint64(63)) != 0
+            r = _draw64_np(skey, np.repeat(i, K), 0, np.tile(np.arange(K, dtype=np.uint64), n))
+            cand = (((r >> np.uint64(32)) * np.uint64(kg.n_entities)) >> np.uint64(32)).astype(np.int64) + kg.entity_base
+        cand = cand.reshape(n, K)
+        srt = np.sort(cand, axis=1)
+        bad = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
+        hs = np.repeat(head_side, K).reshape(n, K)
+        nh = np.where(hs, cand, pos[:, [0]])
+        nt = np.where(hs, pos[:, [2]], cand)
+        nr = np.broadcast_to(pos[:, [1]], (n, K))
+        if kg.set is not None:
+            if not hasattr(kg, "_keys"):
+                arr = np.array(sorted(kg.set), dtype=np.int64)
+                kg._keys = np.sort((arr[:, 0] << 40) | (arr[:, 1] << 24) | arr[:, 2])
+            keys = (nh << 40) | (nr << 24) | nt
+            idx = np.searchsorted(kg._keys, keys.ravel())
+            idx[idx >= len(kg._keys)] = len(kg._keys) - 1
+            bad |= (kg._keys[idx] == keys.ravel()).reshape(n, K).any(axis=1)
+        block = np.stack([nh, nr, nt], axis=2).astype(np.int32)
+        for k in np.nonzero(bad)[0]:
+            h, rr, t = (int(x) for x in pos[k])
+            block[k] = np.asarray(sample_one(kg, h, rr, t, K, skey, int(index_base + off + k)), dtype=np.int32)
+        out[off * K:(off + n) * K] = block.reshape(n * K, 3)
+        off += n
+    return out

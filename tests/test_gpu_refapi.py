@@ -137,6 +137,32 @@ def test_multike_relation_view_epochs_match_oracle(golden, capsys):
         m._define_attribute_view_graph()
 
 
+def test_multike_common_space_epoch_matches_oracle(golden, capsys):
+    """train_common_space_learning_1epo (MultiKE_model.py:458-473) with one batch holding every
+    entity (so the random batch order does not matter) against torch autograd."""
+    from oracle.tf_semantics import l2_normalize
+    m, (n_ent, *_rest) = _fake_model(golden)
+    rng = np.random.default_rng(2)
+    from multike_b200 import tables as T
+    m.name_embeds = T.EmbeddingTable(2 * n_ent, 75, False, "cuda", init=rng.normal(0, 0.1, (2 * n_ent, 75)),
+                                     trainable=False)
+    m.args.entity_batch_size, m.args.ITC_learning_rate, m.args.cv_weight, m.args.cv_name_weight = 10 ** 6, 0.004, 1.0, 1.0
+    m._define_common_space_learning_graph()
+    ents = list(range(0, 2 * n_ent, 3))
+    before = [t.raw().astype(np.float64) for t in (m.ent_embeds, m.rv_ent_embeds, m.av_ent_embeds)]
+    N = torch.tensor(m.name_embeds.raw().astype(np.float64))
+    V = [torch.tensor(b, requires_grad=True) for b in before]
+    F, R, A = (l2_normalize(v, 1)[ents] for v in V)
+    loss = ((F - N[ents]) ** 2).sum() + ((F - R) ** 2).sum() + ((F - A) ** 2).sum()
+    grads = torch.autograd.grad(loss, V)
+    got = m.train_common_space_learning_1epo(1, ents)
+    assert got == pytest.approx(float(loss) / len(ents), rel=1e-5)
+    assert "epoch 1 of common space learning, avg. loss: {:.4f}".format(float(loss) / len(ents)) in capsys.readouterr().out
+    for t, b, g in zip((m.ent_embeds, m.rv_ent_embeds, m.av_ent_embeds), before, grads):
+        want = b - 0.004 * g.numpy() / np.sqrt(0.1 + g.numpy() ** 2)
+        np.testing.assert_allclose(t.raw(), want, rtol=0, atol=2e-6)
+
+
 def test_multike_truncated_neighbours_are_used(golden):
     m, (n_ent, t1, t2, _, _) = _fake_model(golden, batch_size=100, K=5)
     rng = np.random.default_rng(1)
