@@ -204,6 +204,28 @@ int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
                                 const mke_table_t* b, float* acc_b, float lr_b, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Attribute view, the LIVE score of the reference: conv() (MultiKE_model.py:34-63) + the loss of the
+ * attribute graphs (:144-149 weighted; :183 scale 2, no weights; :214-218 weighted) + full backward.
+ *   loss += scale * sum_i w_i log(1 + exp(|E[ih_i] - conv(A[ia_i], V[iv_i])|^2))
+ * ent = av_ent_embeds (normalised view), attr = attr_embeds (raw: "False important!", :96), val =
+ * literal_embeds (constant).  theta / gtheta: the conv() instance's parameters and their gradient
+ * accumulator as ONE flat fp32 vector of mke_attr_cnn_param_count(dim) floats laid out
+ *   gamma[D] beta[D] k1[2][4][1][2] b1[2] k2[2][4][2][2] b2[2] wd[4D][D] bd[D]
+ * (22 777 at D = 75; three independent instances exist in the reference).
+ * Gradient rows go to ent->grad / attr->grad as in the other kernels; gtheta is accumulated (+=).
+ * workspace: mke_attr_cnn_workspace_floats(n, dim) floats.  Phase 2: mke_rows_apply_adagrad for the
+ * tables, mke_dense_apply_adagrad for theta (acc0 = 0.1).
+ * ------------------------------------------------------------------------------------------ */
+int64_t mke_attr_cnn_param_count(int32_t dim);
+int64_t mke_attr_cnn_workspace_floats(int32_t n, int32_t dim);
+int mke_attr_cnn_fwd_bwd(const mke_table_t* ent, const mke_table_t* attr, const mke_table_t* val,
+                         const int32_t* ih, const int32_t* ia, const int32_t* iv, int32_t n,
+                         const float* w_or_null, float scale, const float* theta, float* gtheta,
+                         float* workspace, double* loss_accum, mke_stream_t stream);
+/* dense Adagrad (acc += g^2; theta -= lr g rsqrt(acc); g = 0) for a flat parameter vector */
+int mke_dense_apply_adagrad(float* theta, float* grad, float* acc, int64_t n, float lr, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * ITC cross-view alignment step (MultiKE_model.py:225-239 + losses.py:66-69), fused:
  *   loss += scale * sum_i ( name_weight |F_i - N_i|^2 + |F_i - R_i|^2 + |F_i - A_i|^2 ),  i = idx[.]
  * F = ent_embeds, N = name_embeds (constant: grad NULL), R = rv_ent_embeds, A = av_ent_embeds, each

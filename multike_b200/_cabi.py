@@ -87,6 +87,10 @@ SIGNATURES = {
     "mke_rel_step_structured": (_i32, [_PT, _PT, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rel_step_structured2": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
+    "mke_attr_cnn_param_count": (_c.c_int64, [_i32]),
+    "mke_attr_cnn_workspace_floats": (_c.c_int64, [_i32, _i32]),
+    "mke_attr_cnn_fwd_bwd": (_i32, [_PT, _PT, _PT, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "mke_dense_apply_adagrad": (_i32, [_vp, _vp, _vp, _c.c_int64, _f32, _vp]),
     "mke_align_fwd_bwd": (_i32, [_PT, _PT, _PT, _PT, _vp, _i32, _f32, _f32, _vp, _vp]),
     "mke_dense_logistic_fwd_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mke_dense_sqdist_fwd_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
