@@ -6,9 +6,10 @@ device tables and the kernels behind the C-ABI (multike_b200/relation_view.py). 
 purpose: batches and negatives never leave the device (``steps_tasks`` / ``batch_queue`` are
 accepted and ignored), and the per-epoch print lines are kept verbatim.
 
-Also mirrored: ITC common-space learning (:225-239, :458-473) on the fused alignment kernel.
-Not mirrored yet (SURVEY.md section 8 "next" rows; calling them raises NotImplementedError): the
-attribute-view CNN graphs (MultiKE_model.py:134-151, 172-185, 203-221) and space mapping (:241-261).
+Also mirrored: the three attribute-view CNN graphs (:134-151, :172-185, :203-221) on the conv()
+kernels of csrc/mke_cnn.cu, and ITC common-space learning (:225-239, :458-473) on the fused
+alignment kernel.  Not mirrored yet (calling it raises NotImplementedError): SSL space mapping
+(:241-261, :439-454).
 """
 import math
 import os
@@ -19,7 +20,8 @@ import torch
 
 from multike_b200 import _cabi
 from multike_b200 import tables as T
-from multike_b200.relation_view import RelationView
+from multike_b200.attr_view import AttrCNN
+from multike_b200.relation_view import RelationView, clipped_slice, split_batch
 
 
 def generate_out_folder(out_folder, training_data_path, div_path, method_name):
@@ -122,8 +124,7 @@ class MultiKE:
         self._ckgp_slot = "ckgp_relation"
 
     def _not_yet(self, *a, **k):
-        raise NotImplementedError("attribute-view CNN / common-space / space-mapping graphs are SURVEY.md "
-                                  "section 8 'next' rows; not part of the relation-view hot path")
+        raise NotImplementedError("the SSL space-mapping graph (MultiKE_model.py:241-261) is not built yet")
 
     def _define_common_space_learning_graph(self):
         """MultiKE_model.py:225-239: cv_weight * (cv_name_weight |F-N|^2 + |F-R|^2 + |F-A|^2), Adagrad
@@ -131,13 +132,101 @@ class MultiKE:
         assert self.name_embeds is not None, "the common-space graph needs data.local_name_vectors"
         self._cn_slot = "cross_name"
 
-    _define_attribute_view_graph = _not_yet
-    _define_cross_kg_entity_reference_attribute_view_graph = _not_yet
-    _define_cross_kg_attribute_reference_graph = _not_yet
+    # --- attribute view: conv() score (MultiKE_model.py:34-63), three independent weight sets ------
+    def _new_cnn(self):
+        gen = torch.Generator().manual_seed(self.seed + 1000 + len(getattr(self, "_cnns", [])))
+        cnn = AttrCNN(self.args.dim, self.device, generator=gen)
+        self._cnns = getattr(self, "_cnns", []) + [cnn]
+        return cnn
+
+    def _define_attribute_view_graph(self):
+        """MultiKE_model.py:134-151 (weighted, no negatives: neg_triples_num is the literal 0, :331)"""
+        assert self.literal_embeds is not None, "the attribute view needs data.value_vectors"
+        self._attr_cnn, self._attr_slot = self._new_cnn(), "attribute"
+
+    def _define_cross_kg_entity_reference_attribute_view_graph(self):
+        """MultiKE_model.py:172-185: 2 * sum log(1 + exp(-score)), own conv() weights"""
+        self._ckge_attr_cnn, self._ckge_attr_slot = self._new_cnn(), "ckge_attribute"
+
+    def _define_cross_kg_attribute_reference_graph(self):
+        """MultiKE_model.py:203-221: weighted, own conv() weights"""
+        self._ckga_attr_cnn, self._ckga_attr_slot = self._new_cnn(), "ckga_attribute"
+
+    def _attr_step(self, cnn, slot, rows, acc, weighted, scale):
+        """one session.run([loss, optimizer]) of an attribute graph on device rows [n, 4] (h, a, v, w)"""
+        ih, ia, iv = (rows[:, k].to(torch.int32).contiguous() for k in range(3))
+        w = rows[:, 3].to(torch.float32).contiguous() if weighted else None
+        cnn.fwd_bwd(self.av_ent_embeds, self.attr_embeds, self.literal_embeds, ih, ia, iv, acc, w=w, scale=scale)
+        lr = self.args.learning_rate
+        self.av_ent_embeds.apply_adagrad(slot, lr)
+        self.attr_embeds.apply_adagrad(slot, lr)
+        cnn.apply_adagrad(slot, lr)
+
+    @staticmethod
+    def _rows(triples, device):
+        a = np.asarray(triples, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] == 0:
+            return torch.zeros(0, 4, dtype=torch.float64, device=device)
+        if a.shape[1] == 3:
+            a = np.concatenate([a, np.ones((a.shape[0], 1))], 1)
+        return torch.from_numpy(np.ascontiguousarray(a[:, :4])).to(device)
+
+    def train_attribute_view_1epo(self, epoch, triple_steps, steps_tasks, batch_queue, neighbors1, neighbors2):
+        """MultiKE_model.py:319-345; batches as attr_batch.py:39-50 with neg_triples_num = 0"""
+        start = time.time()
+        pam = self.predicate_align_model
+        r1 = self._rows(pam.attribute_triples_w_weights1, self.device)
+        r2 = self._rows(pam.attribute_triples_w_weights2, self.device)
+        n1, n2 = r1.shape[0], r2.shape[0]
+        b1, b2 = split_batch(n1, n2, self.args.attribute_batch_size)
+        acc = T.new_loss_accumulator(self.device)
+        trained = 0
+        for step in range(triple_steps):
+            (s1, e1), (s2, e2) = clipped_slice(n1, b1, step), clipped_slice(n2, b2, step)
+            rows = torch.cat([r1[s1:e1], r2[s2:e2]])
+            if rows.shape[0] == 0:
+                continue
+            self._attr_step(self._attr_cnn, self._attr_slot, rows, acc, weighted=True, scale=1.0)
+            trained += rows.shape[0]
+        epoch_loss = float(acc.item()) / max(trained, 1)
+        import random
+        random.shuffle(pam.attribute_triples_w_weights1)
+        random.shuffle(pam.attribute_triples_w_weights2)
+        print('epoch {} of att. view, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss, time.time() - start))
+        return epoch_loss
+
+    def _attr_sampled_epoch(self, sup_triples, cnn, slot, weighted, scale):
+        rows = self._rows(sup_triples, self.device)
+        n = rows.shape[0]
+        steps = int(math.ceil(n / self.args.attribute_batch_size))
+        batch_size = self.args.attribute_batch_size if steps > 1 else n
+        acc = T.new_loss_accumulator(self.device)
+        for _ in range(steps):
+            pick = torch.randperm(n, device=self.device)[:batch_size]  # random.sample
+            self._attr_step(cnn, slot, rows[pick], acc, weighted=weighted, scale=scale)
+        return float(acc.item()) / max(steps * batch_size, 1)
+
+    def train_cross_kg_entity_inference_attribute_view_1epo(self, epoch, sup_triples):
+        """MultiKE_model.py:371-391"""
+        if len(sup_triples) == 0:
+            return
+        start = time.time()
+        epoch_loss = self._attr_sampled_epoch(sup_triples, self._ckge_attr_cnn, self._ckge_attr_slot, False, 2.0)
+        print('epoch {} of cross-kg entity inference in attr. view, avg. loss: {:.4f}, time: {:.4f}s'.format(
+            epoch, epoch_loss, time.time() - start))
+        return epoch_loss
+
+    def train_cross_kg_attribute_inference_1epo(self, epoch, sup_triples):
+        """MultiKE_model.py:416-437"""
+        if len(sup_triples) == 0:
+            return
+        start = time.time()
+        epoch_loss = self._attr_sampled_epoch(sup_triples, self._ckga_attr_cnn, self._ckga_attr_slot, True, 1.0)
+        print('epoch {} of cross-kg attribute inference in attr. view, avg. loss: {:.4f}, time: {:.4f}s'.format(
+            epoch, epoch_loss, time.time() - start))
+        return epoch_loss
+
     _define_space_mapping_graph = _not_yet
-    train_attribute_view_1epo = _not_yet
-    train_cross_kg_entity_inference_attribute_view_1epo = _not_yet
-    train_cross_kg_attribute_inference_1epo = _not_yet
     train_shared_space_mapping_1epo = _not_yet
 
     def train_common_space_learning_1epo(self, epoch, entities):

@@ -134,7 +134,68 @@ def test_multike_relation_view_epochs_match_oracle(golden, capsys):
     assert m.eval_kg2_useful_ent_embeddings().shape == (2, 75)
     assert m.rv_ent_embeds.eval(session=m.session).shape == (2 * n_ent, 75)
     with pytest.raises(NotImplementedError):
-        m._define_attribute_view_graph()
+        m._define_space_mapping_graph()
+
+
+def test_multike_attribute_view_epochs_match_oracle(golden, capsys):
+    """train_attribute_view_1epo / ckge-attr / ckga-attr (MultiKE_model.py:319-345, 371-391, 416-437)
+    against the torch oracle of conv(): batches as attr_batch.py builds them (no negatives)."""
+    from oracle import attr_cnn as oc
+    from oracle.tf_semantics import l2_normalize
+    from multike_b200 import tables as T
+    from multike_b200.relation_view import clipped_slice, split_batch
+    m, (n_ent, *_r) = _fake_model(golden)
+    g = golden("ref_batch_attribute.npz")
+    a1 = [(int(h), int(a) % 3, int(v), float(w)) for h, a, v, w in g["a1"]]
+    a2 = [(int(h), int(a) % 3, int(v), float(w)) for h, a, v, w in g["a2"]]
+    n_val = int(max(max(t[2] for t in a1), max(t[2] for t in a2))) + 1
+    rng = np.random.default_rng(4)
+    m.literal_embeds = T.EmbeddingTable(n_val, 75, False, "cuda", init=rng.normal(0, 0.3, (n_val, 75)), trainable=False)
+    m.predicate_align_model = types.SimpleNamespace(attribute_triples_w_weights1=list(a1), attribute_triples_w_weights2=list(a2))
+    m.args.attribute_batch_size = 128
+    m._define_attribute_view_graph()
+    m._define_cross_kg_entity_reference_attribute_view_graph()
+    m._define_cross_kg_attribute_reference_graph()
+    dim, lr = 75, 0.001
+    Ve = torch.tensor(m.av_ent_embeds.raw().astype(np.float64))
+    Va = torch.tensor(m.attr_embeds.raw().astype(np.float64))
+    Vv = torch.tensor(m.literal_embeds.raw().astype(np.float64))
+    th = m._attr_cnn.theta.double().cpu()
+    accs = [torch.full_like(x, 0.1) for x in (Ve, Va, th)]
+    steps = int(np.ceil((len(a1) + len(a2)) / 128))
+    b1, b2 = split_batch(len(a1), len(a2), 128)
+    A1, A2 = np.array(a1), np.array(a2)
+    tot, cnt = 0.0, 0
+    for step in range(steps):
+        (s1, e1), (s2, e2) = clipped_slice(len(a1), b1, step), clipped_slice(len(a2), b2, step)
+        rows = np.concatenate([A1[s1:e1], A2[s2:e2]])
+        ih, ia, iv, w = rows[:, 0].astype(int), rows[:, 1].astype(int), rows[:, 2].astype(int), torch.tensor(rows[:, 3])
+        ve, va, t = Ve.clone().requires_grad_(True), Va.clone().requires_grad_(True), th.clone().requires_grad_(True)
+        loss = oc.attribute_cnn_loss(l2_normalize(ve, 1)[ih], va[ia], Vv[iv], w, t, dim)
+        grads = torch.autograd.grad(loss, [ve, va, t])
+        for x, a, gr in zip((Ve, Va, th), accs, grads):
+            a += gr * gr
+            x -= lr * gr * torch.rsqrt(a)
+        tot += float(loss)
+        cnt += len(rows)
+    got = m.train_attribute_view_1epo(1, steps, None, None, None, None)
+    assert "epoch 1 of att. view, avg. loss: {:.4f}".format(tot / cnt) in capsys.readouterr().out
+    assert got == pytest.approx(tot / cnt, rel=2e-5)
+    np.testing.assert_allclose(m.av_ent_embeds.raw(), Ve.numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(m.attr_embeds.raw(), Va.numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(m._attr_cnn.theta.cpu().numpy(), th.numpy(), rtol=0, atol=2e-5)
+    # cross-KG variants: one batch holding every triple; own conv() weights and Adagrad slots
+    sup = [(h, a, v) for h, a, v, _ in a1[:150]]
+    m.args.attribute_batch_size = 10 ** 6
+    th2 = m._ckge_attr_cnn.theta.double().cpu()
+    P = np.array(sup)
+    ve, t = Ve.clone().requires_grad_(True), th2.clone().requires_grad_(True)
+    ref = oc.attribute_cnn_loss(l2_normalize(ve, 1)[P[:, 0]], Va[P[:, 1]], Vv[P[:, 2]], None, t, dim, scale=2.0)
+    got = m.train_cross_kg_entity_inference_attribute_view_1epo(1, sup)
+    assert got == pytest.approx(float(ref) / len(sup), rel=2e-5)
+    assert not torch.equal(m._ckge_attr_cnn.theta, m._attr_cnn.theta)
+    got = m.train_cross_kg_attribute_inference_1epo(1, a2[:100])
+    assert np.isfinite(got) and got > 0
 
 
 def test_multike_common_space_epoch_matches_oracle(golden, capsys):
