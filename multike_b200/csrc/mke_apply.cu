@@ -123,6 +123,41 @@ __device__ __forceinline__ void q_store(float* __restrict__ row, int sub, const 
   }
 }
 
+// streaming variants (ld/st.global.cs: evict-first in L1 and L2) for data that is touched once per
+// step -- the Adagrad accumulator -- so that it does not push gradient / variable rows out of L2
+template <int FPL>
+__device__ __forceinline__ void q_load_cs(const float* __restrict__ row, int sub, float (&x)[FPL]) {
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(row + (c * 8 + sub) * 4));
+    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+  }
+  const float* tail = row + NV4 * 32 + REM * sub;
+  if constexpr (REM == 2) {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(tail));
+    x[4 * NV4] = v.x; x[4 * NV4 + 1] = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < REM; ++k) x[4 * NV4 + k] = __ldcs(tail + k);
+  }
+}
+template <int FPL>
+__device__ __forceinline__ void q_store_cs(float* __restrict__ row, int sub, const float (&x)[FPL]) {
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c)
+    __stcs(reinterpret_cast<float4*>(row + (c * 8 + sub) * 4),
+           make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+  float* tail = row + NV4 * 32 + REM * sub;
+  if constexpr (REM == 2) {
+    __stcs(reinterpret_cast<float2*>(tail), make_float2(x[4 * NV4], x[4 * NV4 + 1]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < REM; ++k) __stcs(tail + k, x[4 * NV4 + k]);
+  }
+}
+
 struct ApplyTable {
   float* var;
   float* grad;
@@ -132,11 +167,16 @@ struct ApplyTable {
   int normalised;
   float lr;
   int replicas;  // gradient copies to sum and re-zero (mke_table_t.grad_replicas), >= 1
+  int hint;      // bit 0: accumulator rows streamed (evict-first); bit 1: variable rows streamed too
 };
+static int apply_hint() {
+  static const int h = getenv("MKE_APPLY_HINT") ? atoi(getenv("MKE_APPLY_HINT")) : 0;
+  return h;
+}
 static ApplyTable apply_table(const mke_table_t* t, float* acc, float lr) {
   // a row-sharded table is swept shard by shard: this rank's rows only
   return ApplyTable{t->var, t->grad, t->touched, acc, table_local_rows(t), t->normalised, lr,
-                    t->grad_replicas > 1 ? t->grad_replicas : 1};
+                    t->grad_replicas > 1 ? t->grad_replicas : 1, apply_hint()};
 }
 
 // Normalise-backward + Adagrad for the row at float offset `off`, executed by a quarter (lanes with
@@ -147,8 +187,8 @@ __device__ __forceinline__ void apply_one_row(const ApplyTable& T, size_t off, b
   const size_t rep_floats = (size_t)T.rows * stride;
   float g[FPL], v[FPL], a[FPL];
   q_load<FPL>(T.grad + off, sub, g);
-  q_load<FPL>(T.var + off, sub, v);
-  q_load<FPL>(T.acc + off, sub, a);
+  if (T.hint & 2) q_load_cs<FPL>(T.var + off, sub, v); else q_load<FPL>(T.var + off, sub, v);
+  if (T.hint & 1) q_load_cs<FPL>(T.acc + off, sub, a); else q_load<FPL>(T.acc + off, sub, a);
   // gradient copies of small hot tables (mke_table_t.grad_replicas)
   for (int rep = 1; rep < T.replicas; ++rep) {
     float g2[FPL];
@@ -182,8 +222,8 @@ __device__ __forceinline__ void apply_one_row(const ApplyTable& T, size_t off, b
     g[k] = 0.f;
   }
   if (on) {
-    q_store<FPL>(T.var + off, sub, v);
-    q_store<FPL>(T.acc + off, sub, a);
+    if (T.hint & 2) q_store_cs<FPL>(T.var + off, sub, v); else q_store<FPL>(T.var + off, sub, v);
+    if (T.hint & 1) q_store_cs<FPL>(T.acc + off, sub, a); else q_store<FPL>(T.acc + off, sub, a);
     for (int rep = 0; rep < T.replicas; ++rep) q_store<FPL>(T.grad + rep * rep_floats + off, sub, g);
   }
 }
@@ -311,7 +351,7 @@ extern "C" int mke_rows_apply_adagrad(const mke_table_t* table, float* acc, floa
   static const int generic = getenv("MKE_APPLY_GENERIC") ? atoi(getenv("MKE_APPLY_GENERIC")) : 0;
   if (!generic) {
     const ApplyTable A = apply_table(table, acc, lr);
-    const ApplyTable B{nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f, 1};
+    const ApplyTable B{nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f, 1, 0};
     const int rc = dispatch_apply_q8(table->stride, A, B, s);
     if (rc <= 0) return rc;
   }

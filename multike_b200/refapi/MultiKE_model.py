@@ -8,8 +8,8 @@ accepted and ignored), and the per-epoch print lines are kept verbatim.
 
 Also mirrored: the three attribute-view CNN graphs (:134-151, :172-185, :203-221) on the conv()
 kernels of csrc/mke_cnn.cu, and ITC common-space learning (:225-239, :458-473) on the fused
-alignment kernel.  Not mirrored yet (calling it raises NotImplementedError): SSL space mapping
-(:241-261, :439-454).
+alignment kernel, and SSL space mapping (:241-261, :439-454; its 75x75 products go through
+cuBLAS, gradient rows and Adagrad through the kernels).
 """
 import math
 import os
@@ -123,9 +123,6 @@ class MultiKE:
         """MultiKE_model.py:187-201: 2 * logistic_loss_wo_negs (weighted), its own Adagrad slots"""
         self._ckgp_slot = "ckgp_relation"
 
-    def _not_yet(self, *a, **k):
-        raise NotImplementedError("the SSL space-mapping graph (MultiKE_model.py:241-261) is not built yet")
-
     def _define_common_space_learning_graph(self):
         """MultiKE_model.py:225-239: cv_weight * (cv_name_weight |F-N|^2 + |F-R|^2 + |F-A|^2), Adagrad
         with args.ITC_learning_rate and its own accumulator slots"""
@@ -226,8 +223,57 @@ class MultiKE:
             epoch, epoch_loss, time.time() - start))
         return epoch_loss
 
-    _define_space_mapping_graph = _not_yet
-    train_shared_space_mapping_1epo = _not_yet
+    # --- SSL late combination (MultiKE_model.py:241-261, :439-454) --------------------------------
+    def _define_space_mapping_graph(self):
+        """Only variables whose name starts with "shared" train (:257): ent_embeds and the three
+        dim x dim mappings (tf.initializers.orthogonal(), gain 1).  The 75x75 products are plain
+        library GEMMs (cuBLAS via torch); gradient rows and both Adagrad updates use the kernels."""
+        assert self.name_embeds is not None, "the space-mapping graph needs data.local_name_vectors"
+        from multike_b200.refapi import losses as L
+        self._sm_losses = L
+        dim = self.args.dim
+        gen = torch.Generator().manual_seed(self.seed + 77)
+        mats = []
+        for _ in range(3):  # orthogonal initializer: QR of a normal matrix, signs fixed by diag(R)
+            q, r = torch.linalg.qr(torch.randn(dim, dim, generator=gen))
+            mats.append(q * torch.sign(torch.diagonal(r)))
+        self._maps = torch.stack(mats).to(self.device, torch.float32).contiguous()   # nv, rv, av
+        self.nv_mapping, self.rv_mapping, self.av_mapping = self._maps[0], self._maps[1], self._maps[2]
+        self._maps_grad = torch.zeros_like(self._maps)
+        self._maps_acc = torch.full_like(self._maps, T.ADAGRAD_INIT)
+        self.eye_mat = torch.eye(dim, device=self.device)
+        self._sm_slot = "shared_comb"
+
+    def train_shared_space_mapping_1epo(self, epoch, entities):
+        start = time.time()
+        lib = _cabi.load()
+        ents = torch.as_tensor(np.asarray(entities, dtype=np.int32)).to(self.device)
+        n = ents.numel()
+        steps = int(math.ceil(n / self.args.entity_batch_size))
+        batch_size = self.args.entity_batch_size if steps > 1 else n
+        lr, ow = self.args.learning_rate, self.args.orthogonal_weight
+        F_tab = self.ent_embeds
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        for _ in range(steps):
+            idx = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()
+            final = F_tab.export(idx).requires_grad_(True)
+            views = (self.name_embeds.export(idx), self._rv.ent.export(idx), self.av_ent_embeds.export(idx))
+            maps = self._maps.detach().clone().requires_grad_(True)
+            loss = sum(self._sm_losses.space_mapping_loss(x, final, maps[k], self.eye_mat, ow) for k, x in enumerate(views))
+            g_final, g_maps = torch.autograd.grad(loss, [final, maps])
+            F_tab.grad[:, : F_tab.dim].index_add_(0, idx.long(), g_final)   # ids are distinct (random.sample)
+            if F_tab.touched is not None:
+                F_tab.touched[idx.long()] = 1
+            F_tab.apply_adagrad(self._sm_slot, lr)
+            self._maps_grad.copy_(g_maps)
+            _cabi.check(lib.mke_dense_apply_adagrad(self._maps.data_ptr(), self._maps_grad.data_ptr(),
+                                                    self._maps_acc.data_ptr(), self._maps.numel(), float(lr),
+                                                    _cabi.current_stream()))
+            total += loss.detach().double()
+        epoch_loss = float(total) / max(steps * batch_size, 1)
+        print('epoch {} of shared space learning, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss,
+                                                                                           time.time() - start))
+        return epoch_loss
 
     def train_common_space_learning_1epo(self, epoch, entities):
         """MultiKE_model.py:458-473"""

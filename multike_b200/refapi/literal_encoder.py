@@ -1,0 +1,141 @@
+"""Mirror of AutoEncoderModel (code/literal_encoder.py:19-144): the literal auto-encoder
+1500 -> 1024 -> 512 -> dim -> 512 -> 1024 -> 1500, the only true GEMMs of the pipeline.
+
+Same constructor and methods as the reference.  The six affine layers are plain dense GEMMs and run
+on the tensor cores through cuBLAS (torch.matmul, TF32 inputs / fp32 accumulate by default;
+`args.encoder_tf32 = False` keeps full fp32).  All weights and biases live in ONE flat fp32 CUDA
+vector whose Adagrad update is the hand-written dense kernel mke_dense_apply_adagrad
+(acc0 = 0.1, no epsilon [TF semantics]).  No CPU path.
+"""
+import time
+
+import numpy as np
+import torch
+
+from multike_b200 import _cabi
+from multike_b200.tables import ADAGRAD_INIT
+
+
+def _shapes(input_dimension, hidden_dimensions):
+    hds = [input_dimension] + list(hidden_dimensions)
+    n = len(hidden_dimensions)
+    out = []
+    for i in range(n):
+        out += [(hds[i], hds[i + 1]), (hds[i + 1],)]      # encoder_h{i}, encoder_b{i}   (:45-50)
+    for i in range(n):
+        j = n - i
+        out += [(hds[j], hds[j - 1]), (hds[j - 1],)]      # decoder_h{i}, decoder_b{i}   (:51-60)
+    return out
+
+
+def _act(x, kind):
+    if kind == 'sigmoid':
+        return torch.sigmoid(x)
+    if kind == 'tanh':
+        return torch.tanh(x)
+    return x  # the shipped "thah" matches neither branch (:75-78)
+
+
+class AutoEncoderModel:
+    def __init__(self, word_vec_list, args, input_dimension=1500, hidden_dimensions=None, init_params=None,
+                 generator=None):
+        self._lib = _cabi.load()
+        self.session = None
+        self.args = args
+        self.device = torch.device(getattr(args, "device", "cuda"))
+        self.input_dimension = input_dimension
+        if hidden_dimensions is None:
+            hidden_dimensions = [1024, 512, self.args.dim]
+        self.hidden_dimensions = list(hidden_dimensions)
+        self.layer_num = len(self.hidden_dimensions)
+        self.tf32 = bool(getattr(args, "encoder_tf32", True))
+        data = torch.as_tensor(np.reshape(np.asarray(word_vec_list, dtype=np.float32),
+                                          [len(word_vec_list), input_dimension])).to(self.device)
+        if self.args.encoder_normalize:  # sklearn.preprocessing.normalize: unit l2 rows (:34-35)
+            data = data / torch.clamp(data.norm(dim=1, keepdim=True), min=1e-12)
+        self.word_vec_list = data
+        shapes = _shapes(input_dimension, self.hidden_dimensions)
+        total = sum(int(np.prod(s)) for s in shapes)
+        self.theta = torch.empty(total, dtype=torch.float32, device=self.device)
+        if init_params is None:  # tf.random_normal_initializer: N(0, 1) for weights AND biases
+            self.theta.copy_(torch.randn(total, generator=generator).to(self.device))
+        self.grad = torch.zeros_like(self.theta)
+        self.acc = torch.full_like(self.theta, ADAGRAD_INIT)
+        self.params, off = [], 0
+        for k, s in enumerate(shapes):
+            n = int(np.prod(s))
+            view = self.theta[off:off + n].view(*s)
+            if init_params is not None:
+                view.copy_(torch.as_tensor(np.asarray(init_params[k], dtype=np.float32)).to(self.device))
+            self.params.append(view)
+            off += n
+        self.weights = {('encoder_h%d' % i): self.params[2 * i] for i in range(self.layer_num)}
+        self.weights.update({('decoder_h%d' % i): self.params[2 * (self.layer_num + i)] for i in range(self.layer_num)})
+        self.biases = {('encoder_b%d' % i): self.params[2 * i + 1] for i in range(self.layer_num)}
+        self.biases.update({('decoder_b%d' % i): self.params[2 * (self.layer_num + i) + 1] for i in range(self.layer_num)})
+
+    # -- graph ------------------------------------------------------------------------------
+    def encoder(self, input_data, params=None):
+        params = self.params if params is None else params
+        x = input_data
+        for i in range(self.layer_num):
+            x = _act(x @ params[2 * i] + params[2 * i + 1], self.args.encoder_active)
+        return x
+
+    def decoder(self, input_data, params=None):
+        params = self.params if params is None else params
+        x = input_data
+        for i in range(self.layer_num):
+            x = _act(x @ params[2 * (self.layer_num + i)] + params[2 * (self.layer_num + i) + 1], self.args.encoder_active)
+        return x
+
+    def _step(self, batch):
+        """one session.run([loss, optimizer]) (:62-69): mean squared reconstruction error, Adagrad"""
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
+        try:
+            leaves = [p.detach().requires_grad_(True) for p in self.params]
+            code = self.encoder(batch, leaves)
+            if self.args.encoder_normalize:  # tf.nn.l2_normalize without axis: global norm (:66)
+                code = code * torch.rsqrt(torch.clamp((code * code).sum(), min=1e-12))
+            loss = ((self.decoder(code, leaves) - batch) ** 2).mean()
+            grads = torch.autograd.grad(loss, leaves)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        off = 0
+        for g in grads:
+            self.grad[off:off + g.numel()].copy_(g.reshape(-1))
+            off += g.numel()
+        _cabi.check(self._lib.mke_dense_apply_adagrad(self.theta.data_ptr(), self.grad.data_ptr(), self.acc.data_ptr(),
+                                                      self.theta.numel(), float(self.args.learning_rate),
+                                                      _cabi.current_stream()))
+        return loss.detach()
+
+    def train_one_epoch(self, epoch):
+        start_time = time.time()
+        batch_size = self.args.batch_size
+        num_batch = len(self.word_vec_list) // batch_size + 1  # (:96) the last batch may be empty: skipped here
+        loss_sum = torch.zeros((), dtype=torch.float32, device=self.device)
+        for i in range(num_batch):
+            batch = self.word_vec_list[i * batch_size:(i + 1) * batch_size]
+            if batch.shape[0] == 0:
+                continue
+            loss_sum += self._step(batch)
+        loss_sum = float(loss_sum) + self.args.batch_size  # sic (:106)
+        print('epoch {} of literal encoder, loss: {:.4f}, time: {:.4f}s'.format(epoch, loss_sum, time.time() - start_time))
+        return loss_sum
+
+    def encoder_multi_batches(self, input_data):
+        """:114-144: the final encoding, float64, on the raw (un-normalised) inputs"""
+        print('encode literal embeddings...', len(input_data))
+        x = torch.as_tensor(np.reshape(np.asarray(input_data, dtype=np.float64), [len(input_data), self.input_dimension]))
+        out = np.zeros((len(input_data), self.hidden_dimensions[-1]))
+        batch_size = self.args.batch_size
+        params = [p.double() for p in self.params[:2 * self.layer_num]]
+        for a in range(0, len(input_data), batch_size):
+            h = x[a:a + batch_size].to(self.device)
+            for i in range(self.layer_num):
+                h = _act(h @ params[2 * i] + params[2 * i + 1], self.args.encoder_active)
+            out[a:a + batch_size] = h.cpu().numpy()
+        print("encoded literal embeddings", out.shape)
+        return out

@@ -133,8 +133,6 @@ def test_multike_relation_view_epochs_match_oracle(golden, capsys):
     assert e1.shape == (n_ent, 75) and np.allclose(np.linalg.norm(e1, axis=1), 1.0, atol=1e-5)
     assert m.eval_kg2_useful_ent_embeddings().shape == (2, 75)
     assert m.rv_ent_embeds.eval(session=m.session).shape == (2 * n_ent, 75)
-    with pytest.raises(NotImplementedError):
-        m._define_space_mapping_graph()
 
 
 def test_multike_attribute_view_epochs_match_oracle(golden, capsys):
@@ -224,6 +222,38 @@ def test_multike_common_space_epoch_matches_oracle(golden, capsys):
         np.testing.assert_allclose(t.raw(), want, rtol=0, atol=2e-6)
 
 
+def test_multike_space_mapping_epoch_matches_oracle(golden):
+    """train_shared_space_mapping_1epo (MultiKE_model.py:439-454): only ent_embeds and the three
+    mappings move; one batch with every entity against torch autograd (float64)."""
+    from oracle import losses as ol
+    from oracle.tf_semantics import l2_normalize
+    from multike_b200 import tables as T
+    m, (n_ent, *_r) = _fake_model(golden)
+    rng = np.random.default_rng(6)
+    m.name_embeds = T.EmbeddingTable(2 * n_ent, 75, False, "cuda", init=rng.normal(0, 0.1, (2 * n_ent, 75)), trainable=False)
+    m.args.entity_batch_size, m.args.orthogonal_weight = 10 ** 6, 2
+    m._define_space_mapping_graph()
+    ents = list(range(1, 2 * n_ent, 2))
+    F0 = m.ent_embeds.raw().astype(np.float64)
+    rv0, av0 = m.rv_ent_embeds.raw().copy(), m.av_ent_embeds.raw().copy()
+    maps0 = m._maps.double().cpu()
+    assert torch.allclose(maps0[0] @ maps0[0].T, torch.eye(75, dtype=torch.float64), atol=1e-5)   # orthogonal init
+    V = torch.tensor(F0, requires_grad=True)
+    M = maps0.clone().requires_grad_(True)
+    Fv = l2_normalize(V, 1)[ents]
+    X = [torch.tensor(m.name_embeds.raw().astype(np.float64))[ents],
+         l2_normalize(torch.tensor(rv0.astype(np.float64)), 1)[ents], l2_normalize(torch.tensor(av0.astype(np.float64)), 1)[ents]]
+    eye = torch.eye(75, dtype=torch.float64)
+    loss = sum(ol.space_mapping_loss(x, Fv, M[k], eye, 2) for k, x in enumerate(X))
+    gV, gM = torch.autograd.grad(loss, [V, M])
+    got = m.train_shared_space_mapping_1epo(1, ents)
+    assert got == pytest.approx(float(loss) / len(ents), rel=1e-4)
+    np.testing.assert_allclose(m.ent_embeds.raw(), F0 - 0.001 * gV.numpy() / np.sqrt(0.1 + gV.numpy() ** 2), rtol=0, atol=5e-6)
+    np.testing.assert_allclose(m._maps.cpu().numpy(), maps0.numpy() - 0.001 * gM.numpy() / np.sqrt(0.1 + gM.numpy() ** 2),
+                               rtol=0, atol=5e-6)
+    assert np.array_equal(m.rv_ent_embeds.raw(), rv0) and np.array_equal(m.av_ent_embeds.raw(), av0)  # not "shared*"
+
+
 def test_multike_truncated_neighbours_are_used(golden):
     m, (n_ent, t1, t2, _, _) = _fake_model(golden, batch_size=100, K=5)
     rng = np.random.default_rng(1)
@@ -242,3 +272,31 @@ def test_multike_truncated_neighbours_are_used(golden):
     with pytest.raises(AssertionError):
         from multike_b200.refapi.MultiKE_model import MultiKE
         MultiKE(m.data, types.SimpleNamespace(alignment_module='mapping', output='', training_data='x'), None)
+
+
+@pytest.mark.parametrize("tf32,tol", [(False, 1e-5), (True, 2e-3)])
+def test_literal_autoencoder_matches_oracle(tf32, tol, capsys):
+    """AutoEncoderModel (literal_encoder.py:19-144): GEMMs on the tensor cores through cuBLAS, the
+    Adagrad update on the hand-written dense kernel; two epochs against the float64 oracle."""
+    from multike_b200.refapi.literal_encoder import AutoEncoderModel
+    from oracle import autoencoder as oa
+    rng = np.random.default_rng(0)
+    n, d_in, hidden = 230, 96, [64, 32, 16]
+    data = rng.normal(0, 1, (n, d_in))
+    init = [rng.normal(0, 1, s) for s in oa.shapes(d_in, hidden)]
+    args = types.SimpleNamespace(dim=16, encoder_normalize=True, encoder_active="thah", learning_rate=0.01, batch_size=50,
+                                 encoder_tf32=tf32)
+    m = AutoEncoderModel(data, args, input_dimension=d_in, hidden_dimensions=list(hidden), init_params=init)
+    o = oa.AutoEncoderOracle(init, 3, active="thah", normalize=True, lr=0.01)
+    rows = data / np.linalg.norm(data, axis=1, keepdims=True)
+    for epoch in (1, 2):
+        want = sum(o.step(rows[a:a + 50]) for a in range(0, n, 50)) + 50
+        got = m.train_one_epoch(epoch)
+        assert got == pytest.approx(want, rel=tol)
+        assert "epoch %d of literal encoder, loss: " % epoch in capsys.readouterr().out
+    for p, q in zip(m.params, o.params):
+        np.testing.assert_allclose(p.cpu().numpy(), q.numpy(), rtol=0, atol=50 * tol)
+    enc = m.encoder_multi_batches(data)
+    want_enc = o.encode(data)   # values of order 1e2 (N(0,1) weights): tolerance relative to the largest code
+    np.testing.assert_allclose(enc, want_enc, rtol=0, atol=(1e-3 if tf32 else 1e-5) * np.abs(want_enc).max())
+    assert set(m.weights) == {"encoder_h0", "encoder_h1", "encoder_h2", "decoder_h0", "decoder_h1", "decoder_h2"}
