@@ -347,7 +347,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "entities": kgs["n_ent"], "relations": kgs["n_rel"],
                        "triples": int(rv.n1 + rv.n2), "dim": dim, "batch": B, "neg": K, "steps_per_epoch": spe,
-                       "variant": ["q8_ldg_red", "tma_bulk", "warp_ldg_red"][args.variant],
+                       "variant": ["q8_ldg_red", "tma_bulk", "warp_ldg_red", "q8_row_stream"][args.variant],
                        "l2": "no flush: step working set (var+grad+Adagrad slot of the entity table, %d MB) exceeds "
                              "the 126 MB L2 and each step touches a different random row set"
                              % (3 * kgs["n_ent"] * rv.ent.stride * 4 // 2 ** 20),

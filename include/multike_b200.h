@@ -149,7 +149,9 @@ int mke_triple_fwd_bwd(const mke_table_t* head, const mke_table_t* mid, const mk
  *               (what base/batch.py:116 returns) -- for parity tests; NULL in production
  *   variant     0 = quarter-warp register path (default; falls back to 2 for strides without an
  *               instantiation), 1 = TMA bulk-copy / bulk-reduce path, 2 = warp-per-positive
- *               LDG / RED.v4 path (any stride <= 256)
+ *               LDG / RED.v4 path (any stride <= 256), 3 = variant 0's arithmetic on the persistent
+ *               row-stream schedule (pre-drawn negatives with 3 + K >= 8; other launch shapes run
+ *               as variant 0)
  */
 int mke_rel_step_sampled(const mke_table_t* ent, const mke_table_t* rel,
                          const int32_t* pos1, int32_t len1, const mke_kg_sampler_t* kg1,

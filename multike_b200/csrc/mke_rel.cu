@@ -517,6 +517,11 @@ static int launch_rel(RelStepParams& p, int variant, cudaStream_t stream) {
   const int n = p.len1 + p.len2;
   if (n <= 0) return 0;
   const int nv = (p.nchunk + 31) / 32;
+  if (variant == 3) {  // persistent row-stream schedule; launch shapes it does not cover use variant 0
+    const int rc = launch_rel_q8p(p, 0, stream);
+    if (rc <= 0) return rc;
+    variant = 0;
+  }
   if (variant == 0) {
     const int rc = launch_rel_q8(p, stream);
     if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = no instantiation for this stride

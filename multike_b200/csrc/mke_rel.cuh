@@ -91,5 +91,7 @@ __device__ __forceinline__ float* rel_grad_replica(const RelStepParams& p) {
 
 // quarter-warp kernel (mke_rel_q8.cu); returns 1 when the stride has no instantiation
 int launch_rel_q8(const RelStepParams& p, cudaStream_t stream);
+// persistent row-stream schedule of the same kernel (mke_rel_q8p.cu); returns 1 when the launch shape is not covered
+int launch_rel_q8p(const RelStepParams& p, int cfg, cudaStream_t stream);
 
 }  // namespace mke

@@ -28,8 +28,9 @@ def G():
     return gpu_util, tables
 
 
-# variant 0 = quarter-warp kernel (default), 1 = TMA bulk copy/reduce, 2 = warp-per-positive LDG/RED
-CASES = [(f, v) for f in ("relation_step_d75.npz", "relation_step_d128.npz") for v in (0, 1, 2)]
+# variant 0 = quarter-warp kernel (default), 1 = TMA bulk copy/reduce, 2 = warp-per-positive LDG/RED,
+# 3 = quarter-warp kernel on the persistent row-stream schedule (mke_rel_q8p.cu)
+CASES = [(f, v) for f in ("relation_step_d75.npz", "relation_step_d128.npz") for v in (0, 1, 2, 3)]
 
 
 @pytest.mark.parametrize("fname,variant", CASES)
@@ -74,7 +75,42 @@ def test_fused_structured_step_matches_golden(G, golden, fname, variant):
     np.testing.assert_allclose(rel.raw(), g["rel3"], rtol=0, atol=3 * ROW_ATOL)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("grid", [1, 2, 3])
+@pytest.mark.parametrize("fname", ["relation_step_d75.npz", "relation_step_d128.npz"])
+def test_row_stream_schedule_many_passes(G, golden, monkeypatch, fname, grid):
+    """Variant 3 with a forced grid of 1-3 blocks (12 quarters each): every quarter walks up to 4
+    positives through the shared-memory ring, incl. idle quarters in the last pass and the
+    double-buffered id lists -- same gradients, loss and flags as the golden step."""
+    U, T = G
+    g = golden(fname)
+    K, lr = int(g["K"]), float(g["lr"])
+    monkeypatch.setenv("MKE_Q8P_GRID", str(grid))
+    ent, rel = U.make_tables(g["ent0"], g["rel0"])
+    acc = T.new_loss_accumulator()
+    T.rel_step_structured(ent, rel, g["pos"], g["neg_ent"], g["neg_side"], K, acc, variant=3)
+    assert U.loss_value(acc) == pytest.approx(float(g["loss"]), rel=LOSS_RTOL)
+    np.testing.assert_allclose(U.grad_np(ent), g["view_grad_ent"], rtol=GRAD_RTOL, atol=GRAD_ATOL)
+    np.testing.assert_allclose(U.grad_np(rel), g["view_grad_rel"], rtol=GRAD_RTOL, atol=GRAD_ATOL)
+    touched = ent.touched.cpu().numpy().astype(bool)
+    want = np.zeros(ent.rows, bool)
+    want[g["pos"][:, [0, 2]].ravel()] = True
+    want[g["neg_ent"].ravel()] = True
+    assert np.array_equal(touched, want)
+    # mixed-side negatives (caller-supplied batches may mix sides inside one positive)
+    side = g["neg_side"].copy()
+    side[::3] ^= 0b1010010
+    outs = []
+    for variant in (0, 3):
+        ent, rel = U.make_tables(g["ent0"], g["rel0"])
+        acc = T.new_loss_accumulator()
+        T.rel_step_structured(ent, rel, g["pos"], g["neg_ent"], side, K, acc, variant=variant)
+        outs.append((U.loss_value(acc), U.grad_np(ent), U.grad_np(rel)))
+    assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=GRAD_RTOL, atol=GRAD_ATOL)
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=GRAD_RTOL, atol=GRAD_ATOL)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("flags,rel_replicas", [((False, False), 1), ((True, False), 5), ((None, None), None),
                                                 ((True, True), 3)])
 def test_step_without_touched_flags(G, golden, variant, flags, rel_replicas):
@@ -470,6 +506,37 @@ def test_full_size_linearity_and_variant_agreement(G, full):
     T.triple_fwd_bwd(ent, rel, ent, neg[:, 0], neg[:, 1], neg[:, 2], acc, negative=True)
     assert U.loss_value(acc) == pytest.approx(outs[0][0], rel=1e-6)
     torch.testing.assert_close(ent.grad_sum(), outs[0][1], rtol=1e-4, atol=2e-5)
+
+
+def test_full_size_row_stream_schedule_equals_one_wave_kernel(G, full):
+    """BASELINE config 2 batch (20 000 positives, two passes per quarter): the persistent
+    row-stream schedule (variant 3) and the one-wave kernel (variant 0) on the same pre-drawn
+    negatives -- same loss, gradient rows, touched flags; then one Adagrad apply each."""
+    U, T = G
+    kgs, ent0, rel0, kg1, kg2 = full
+    K, B1, B2, lr = 10, 10159, 9841, 0.001
+    p1 = torch.as_tensor(kgs["triples1"][2 * B1:3 * B1]).cuda()
+    p2 = torch.as_tensor(kgs["triples2"][2 * B2:3 * B2]).cuda()
+    neg_ent, neg_side = T.sample_structured(p1, kg1, p2, kg2, K, 11, 5)
+    pos = torch.cat([p1, p2])
+    res = []
+    for variant in (0, 3):
+        ent, rel = U.make_tables(ent0.numpy(), rel0.numpy(), rel_replicas=7 if variant == 3 else 1,
+                                 flags=(True, variant == 0))
+        acc = T.new_loss_accumulator()
+        T.rel_step_structured(ent, rel, pos, neg_ent, neg_side, K, acc, variant=variant)
+        loss = U.loss_value(acc)
+        ge, gr, fl = ent.grad_sum().clone(), rel.grad_sum().clone(), ent.touched.clone()
+        T.apply_adagrad_pair(ent, ent.adagrad_slot("r"), lr, rel, rel.adagrad_slot("r"), lr)
+        torch.cuda.synchronize()
+        res.append((loss, ge, gr, fl, ent.var.clone(), rel.var.clone()))
+    a, b = res
+    assert a[0] == pytest.approx(b[0], rel=1e-6)
+    torch.testing.assert_close(a[1], b[1], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(a[2], b[2], rtol=1e-4, atol=2e-4)
+    assert torch.equal(a[3], b[3])
+    torch.testing.assert_close(a[4], b[4], rtol=0, atol=ROW_ATOL)
+    torch.testing.assert_close(a[5], b[5], rtol=0, atol=1e-5)
 
 
 def test_pair_apply_equals_two_single_applies(G, golden):
