@@ -37,6 +37,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "dwy100k_rel_d75_b20000_k10"
 FALLBACK_HBM_GBS = 6650.0
+P1_KERNEL = ["rel_fused_q8_kernel", "rel_fused_tma_kernel", "rel_fused_ldg_kernel", "rel_fused_q8p_kernel"]
 
 
 def bytes_per_positive(dim, K):
@@ -245,7 +246,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=46)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("MKE_VARIANT", "0")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("MKE_VARIANT", "3")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="draw negatives inside the fused kernel")
     ap.add_argument("--cpu-steps", type=int, default=8)
@@ -360,9 +361,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload, "rel_fused_q8_kernel") if args.variant == 0 else None,
+                         "traffic": ncu_traffic(args.workload, P1_KERNEL[args.variant]),
                          "traffic_note": "dram bytes per launch, ncu --set full (cold L2), profiles/r1_traffic.json",
-                         "algorithmic_bytes": alg_bytes, "kernel": "rel_fused_q8_kernel (phase 1)",
+                         "algorithmic_bytes": alg_bytes, "kernel": P1_KERNEL[args.variant] + " (phase 1)",
                          "peak_source": peak_kind, "launch_ms": p1_ms,
                          "bytes_per_positive": bytes_per_positive(dim, K)},
         }

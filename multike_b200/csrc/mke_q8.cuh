@@ -86,36 +86,53 @@ static __device__ __noinline__ float odd_negative(const float* vh, const float* 
                                                   const float* ve, float* gh, float* gr, float* gt, float* ge,
                                                   int ent_norm, int rel_norm, bool head_side, bool on,
                                                   int sub) {
-  float xh[FPL], xr[FPL], xt[FPL], xe[FPL];
-  load_row<FPL>(vh, sub, xh);
-  load_row<FPL>(vr, sub, xr);
-  load_row<FPL>(vt, sub, xt);
-  load_row<FPL>(ve, sub, xe);
-  float sh = sumsq<FPL>(xh), sr = sumsq<FPL>(xr), st = sumsq<FPL>(xt), se = sumsq<FPL>(xe);
+  // One float at a time, three sweeps over the rows (norms, distance, reductions): this path runs
+  // for about 0.2 % of the positives and must not set the register budget of the kernels.
+  constexpr int NV4 = FPL / 4, REM = FPL % 4;
+  auto off = [&](int k) { return k < 4 * NV4 ? 32 * (k >> 2) + 4 * sub + (k & 3) : 32 * NV4 + REM * sub + (k - 4 * NV4); };
+  float sh = 0.f, sr = 0.f, st = 0.f, se = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < FPL; ++k) {
+    const int o = off(k);
+    const float a = __ldg(vh + o), b = __ldg(vr + o), c = __ldg(vt + o), d = __ldg(ve + o);
+    sh = fmaf(a, a, sh);
+    sr = fmaf(b, b, sr);
+    st = fmaf(c, c, st);
+    se = fmaf(d, d, se);
+  }
   qsum3(sh, sr, st);
   se = qsum(se);
   const float ih = ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
   const float ir = rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
   const float it = ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
   const float ie = ent_norm ? rsqrtf(fmaxf(se, kNormEps)) : 1.f;
-  float nd[FPL], sn = 0.f;
-#pragma unroll
+  auto dist = [&](int o) {
+    const float rr = __ldg(vr + o) * ir;
+    return head_side ? (fmaf(__ldg(ve + o), ie, rr) - __ldg(vt + o) * it)
+                     : (fmaf(__ldg(vh + o), ih, rr) - __ldg(ve + o) * ie);
+  };
+  float sn = 0.f;
+#pragma unroll 1
   for (int k = 0; k < FPL; ++k) {
-    const float rr = xr[k] * ir;
-    nd[k] = head_side ? (fmaf(xe[k], ie, rr) - xt[k] * it) : (fmaf(xh[k], ih, rr) - xe[k] * ie);
-    sn = fmaf(nd[k], nd[k], sn);
+    const float nd = dist(off(k));
+    sn = fmaf(nd, nd, sn);
   }
   sn = qsum(sn);
   float lneg, sg;
   softplus_sigmoid(-sn, lneg, sg);
   if (!on) return 0.f;
   const float cn = -2.f * sg;
-  red_row<FPL>(gr, sub, nd, cn);
-  red_row<FPL>(ge, sub, nd, head_side ? cn : -cn);
-  if (head_side)
-    red_row<FPL>(gt, sub, nd, -cn);
-  else
-    red_row<FPL>(gh, sub, nd, cn);
+#pragma unroll 1
+  for (int k = 0; k < FPL; ++k) {
+    const int o = off(k);
+    const float g = cn * dist(o);
+    red_add_f1(gr + o, g);
+    red_add_f1(ge + o, head_side ? g : -g);
+    if (head_side)
+      red_add_f1(gt + o, -g);
+    else
+      red_add_f1(gh + o, g);
+  }
   return lneg;
 }
 
@@ -174,6 +191,21 @@ struct Stage {
       cp_async4(tail(slot), t);
       cp_async4(tail(slot) + 4, t + 1);
       cp_async4(tail(slot) + 8, t + 2);
+    }
+  }
+  // 16-byte piece c (< NV4) of this lane's part of the row in `slot`
+  __device__ __forceinline__ void read4(int slot, int c, float (&v)[4]) const {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                 : "r"(chunk(slot, c)));
+  }
+  // the FPL % 4 floats after the 16-byte pieces
+  __device__ __forceinline__ void read_tail(int slot, float (&v)[REM > 0 ? REM : 1]) const {
+    if constexpr (REM == 2)
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(tail(slot)));
+    if constexpr (REM == 1 || REM == 3) {
+#pragma unroll
+      for (int k = 0; k < REM; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(tail(slot) + 4 * k));
     }
   }
   __device__ __forceinline__ void read(int slot, float (&x)[FPL]) const {

@@ -24,8 +24,16 @@ constexpr int kIdStride = 36;  // h r t + MKE_MAX_NEG ids + side word; 2*36 = 8 
 constexpr int kQ8pThreads = 96;
 constexpr int kQ8pWarps = kQ8pThreads / 32;
 
+// register cap for MINB resident blocks: each of the 4 SM sub-partitions owns 16 384 registers and
+// gets ceil(3 MINB / 4) of the warps
+constexpr int q8p_max_regs(int minb) {
+  const int per_smsp = (kQ8pWarps * minb + 3) / 4;
+  const int r = ((16384 / (per_smsp * 32)) / 8) * 8;
+  return r > 255 ? 248 : r;
+}
+
 template <int FPL, int D, int MINB, bool CG>
-__global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(((65536 / (kQ8pThreads * MINB)) / 8) * 8) rel_fused_q8p_kernel(const RelStepParams p, const int passes) {
+__global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) rel_fused_q8p_kernel(const RelStepParams p, const int passes) {
   constexpr int WARPS = kQ8pWarps;
   constexpr int stride = FPL * 8;
   using Ring = Stage<FPL, D>;
@@ -107,42 +115,64 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(((65536 / (kQ8pThread
     float base[FPL], acc[FPL];
     float bb = 0.f;  // |base|^2
     {
-      float xh[FPL], xr[FPL], xt[FPL];
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, xh);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
-      float sh = sumsq<FPL>(xh);
-      issue_next();
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, xr);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
-      float sr = sumsq<FPL>(xr);
-      issue_next();
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, xt);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
-      float st = sumsq<FPL>(xt);
-      issue_next();
+      // the three rows stay in their ring slots and are read twice (norms first, then the
+      // distance piece by piece): only base/acc and one piece of each row are ever live
+      constexpr int NV4 = FPL / 4, REM = FPL % 4;
+      cp_async_wait<D - 3>();
+      const int s0 = cons_slot;
+      const int s1 = (s0 + 1 == D) ? 0 : s0 + 1;
+      const int s2 = (s1 + 1 == D) ? 0 : s1 + 1;
+      cons_slot = (s2 + 1 == D) ? 0 : s2 + 1;
+      float sh, sr, st;
+      {
+        float x[FPL];
+        stg.read(s0, x);
+        sh = sumsq<FPL>(x);
+        stg.read(s1, x);
+        sr = sumsq<FPL>(x);
+        stg.read(s2, x);
+        st = sumsq<FPL>(x);
+      }
       qsum3(sh, sr, st);
       const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
       const float ir = p.rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
       const float it = p.ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
       float sp = 0.f;
-#pragma unroll
-      for (int k = 0; k < FPL; ++k) {
-        const float hh = xh[k] * ih, tt = xt[k] * it;
-        const float pd = fmaf(xr[k], ir, hh) - tt;  // pos_distance (losses.py:5)
+      auto piece = [&](int k, float xh, float xr, float xt) {
+        const float hh = xh * ih, tt = xt * it;
+        const float pd = fmaf(xr, ir, hh) - tt;  // pos_distance (losses.py:5)
         sp = fmaf(pd, pd, sp);
         acc[k] = pd;
         // head side: nd = e^ + (r^ - t^) = e^ + (pd - h^);  tail side: nd = (h^ + r^) - e^ = (pd + t^) - e^
         base[k] = side0 ? (pd - hh) : (pd + tt);
         bb = fmaf(base[k], base[k], bb);
+      };
+#pragma unroll
+      for (int c = 0; c < NV4; ++c) {
+        float vh[4], vr[4], vt[4];
+        stg.read4(s0, c, vh);
+        stg.read4(s1, c, vr);
+        stg.read4(s2, c, vt);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) piece(4 * c + k, vh[k], vr[k], vt[k]);
+      }
+      if constexpr (REM > 0) {
+        float vh[REM], vr[REM], vt[REM];
+        stg.read_tail(s0, vh);
+        stg.read_tail(s1, vr);
+        stg.read_tail(s2, vt);
+#pragma unroll
+        for (int k = 0; k < REM; ++k) piece(4 * NV4 + k, vh[k], vr[k], vt[k]);
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
         sp += __shfl_xor_sync(kFull, sp, o);
         bb += __shfl_xor_sync(kFull, bb, o);
       }
+      // the three slots are free: the stream moves on by three rows
+      issue_next();
+      issue_next();
+      issue_next();
       float lpos, sg;
       softplus_sigmoid(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
       const float wgt = (p.w != nullptr && active ? __ldg(p.w + i) : 1.f) * p.pos_scale;
@@ -289,11 +319,11 @@ int launch_rel_q8p(const RelStepParams& p, int cfg, cudaStream_t stream) {
   case STRIDE:                                                                   \
     if (d4) return cg ? launch_q8p<FPL, 4, MINB, true>(p, stream) : launch_q8p<FPL, 4, MINB, false>(p, stream); \
     return cg ? launch_q8p<FPL, 6, MINB, true>(p, stream) : launch_q8p<FPL, 6, MINB, false>(p, stream);
-    MKE_Q8P_CASE(32, 4, 8)
+    MKE_Q8P_CASE(32, 4, 6)
     MKE_Q8P_CASE(64, 8, 6)
     MKE_Q8P_CASE(80, 10, 6)
     MKE_Q8P_CASE(104, 13, 5)
-    MKE_Q8P_CASE(128, 16, 4)
+    MKE_Q8P_CASE(128, 16, 5)
 #undef MKE_Q8P_CASE
     default: return 1;
   }

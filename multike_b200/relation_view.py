@@ -40,7 +40,7 @@ class RelationView:
     SLOT = "relation"  # one Adagrad accumulator set per loss graph (MultiKE_model.py:28-31)
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size=5000, neg_num=10,
-                 lr=0.001, seed=0, device="cuda", variant=0, ent_init=None, rel_init=None,
+                 lr=0.001, seed=0, device="cuda", variant=3, ent_init=None, rel_init=None,
                  filter1=None, filter2=None, generator=None, pipelined=True, entities1=None, entities2=None):
         self._lib = _cabi.load()
         self.device = torch.device(device)

@@ -16,6 +16,7 @@
 The pure index arithmetic lives in module-level functions so that it is testable on CPU (gloo).
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -218,9 +219,12 @@ class ShardedRelationView:
     SLOT = "relation"
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size, neg_num, lr, seed, group,
-                 ent_init=None, rel_init=None, filter1=None, filter2=None, rel_replicas=1, by_kg=True):
+                 ent_init=None, rel_init=None, filter1=None, filter2=None, rel_replicas=1, by_kg=True,
+                 variant=None):
         import torch.distributed as dist
         self._lib = _cabi.load()
+        # phase-1 schedule (include/multike_b200.h `variant`); MKE_SHARDED_VARIANT is an experiment knob
+        self.variant = int(os.environ.get("MKE_SHARDED_VARIANT", "0")) if variant is None else int(variant)
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -277,7 +281,7 @@ class ShardedRelationView:
                 ev[0].record()
             _cabi.check(self._lib.mke_rel_step_structured2(
                 self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent.data_ptr(), self._neg_side.data_ptr(),
-                None, 1.0, self.loss_acc.data_ptr(), 0, stream))
+                None, 1.0, self.loss_acc.data_ptr(), self.variant, stream))
             if ev is not None:
                 ev[1].record()
                 self.phase1_events.append(ev)
