@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MKE_ABI_VERSION 3
+#define MKE_ABI_VERSION 4
 #define MKE_EINVAL (-100000)
 #define MKE_MAX_NEG 32        /* K (negatives per positive) supported by the fused kernel */
 #define MKE_MAX_TRY 10        /* base/batch.py:86 max_try=10 */
@@ -374,6 +374,57 @@ int mke_peer_free(void* ptr);
 int mke_ipc_export(const void* ptr, unsigned char handle[64]);   /* cudaIpcGetMemHandle             */
 int mke_ipc_open(const unsigned char handle[64], void** ptr);    /* cudaIpcOpenMemHandle            */
 int mke_ipc_close(void* ptr);
+
+/* ------------------------------------------------------------------------------------------
+ * Similarity search on dense fp32 rows (evaluation and truncated-epsilon neighbours).
+ * Inputs are row-major [*, stride] device arrays of which the first `dim` columns count
+ * (dim <= 128); idx_or_null gathers rows (NULL => rows 0..n-1 in order); normalize != 0 divides
+ * every gathered row by its l2 norm first (sklearn.preprocessing.normalize, base/similarity.py:
+ * 31-33; a zero row stays zero).  Sims are fp32 inner products accumulated in ascending column
+ * order of the embedding (one fmaf chain per pair), so bit-equal rows give bit-equal sims.
+ * ------------------------------------------------------------------------------------------ */
+
+/* floats of workspace mke_sim_rank needs (prepared copies of both row sets + per-row scratch) */
+int64_t mke_sim_rank_workspace_floats(int32_t n1, int32_t n2, int32_t dim);
+
+/*
+ * The Hits@k / MR / MRR evaluator without the similarity matrix.  Replaces
+ * base/similarity.py:9-52 sim(metric='inner'), base/alignment.py:8-79 greedy_alignment and
+ * :141-163 calculate_rank (callers: base/evaluation.py:6-28 valid/test from MultiKE_Late.py:14-61).
+ *   gold_or_null  [n1] column (row of emb2 after the gather) aligned with each row of emb1;
+ *                 NULL => gold[i] = i (what calculate_rank assumes)
+ *   rank_out      [n1] number of columns ranked before the gold one in the stable descending
+ *                 order of the sims: #{j : s_ij > s_ig} + #{j < g : s_ij == s_ig}
+ *                 (rank_index of alignment.py:153; Hits@k <=> rank < k, MR = mean(rank + 1))
+ *   top1_out      [n1] arg max_j s_ij, smallest column on ties (rank[0] of alignment.py:151,
+ *                 the "alignment_rest" pairs)
+ */
+int mke_sim_rank(const float* emb1, const int32_t* idx1_or_null, int32_t n1,
+                 const float* emb2, const int32_t* idx2_or_null, int32_t n2,
+                 int32_t stride, int32_t dim, int32_t normalize, const int32_t* gold_or_null,
+                 float* workspace, int32_t* rank_out, int32_t* top1_out, mke_stream_t stream);
+
+/* floats of workspace for mke_sim_topk when `chunk_rows` rows of sims are materialised at a time */
+int64_t mke_sim_topk_workspace_floats(int32_t n, int32_t dim, int32_t chunk_rows);
+
+/*
+ * Truncated-epsilon candidate lists: for every gathered row i its k most similar rows (itself
+ * included, as in the reference).  Replaces base/batch.py:119-150 generate_neighbours /
+ * find_neighbours (np.matmul + np.argpartition in 4 processes; caller MultiKE_CSL.py:89-99).
+ *   id_list_or_null / id_base   entity id of column c: id_list[c], or id_base + c
+ *   out_rows_or_null            row of neighbours_out that receives the list of gathered row i
+ *                               (NULL => row i); with out_rows = the entity ids the output is the
+ *                               table mke_kg_sampler_t.neighbours expects
+ *   neighbours_out              [*, k] int32; a list holds the k best columns in ASCENDING column
+ *                               order (ties at the k-th sim: smallest columns first) --
+ *                               deterministic where np.argpartition's order is unspecified
+ *   workspace, workspace_floats at least mke_sim_topk_workspace_floats(n, dim, 128); more
+ *                               workspace => more rows of sims per pass
+ */
+int mke_sim_topk(const float* emb, const int32_t* idx_or_null, int32_t n, int32_t stride, int32_t dim,
+                 int32_t normalize, int32_t k, const int32_t* id_list_or_null, int32_t id_base,
+                 const int32_t* out_rows_or_null, float* workspace, int64_t workspace_floats,
+                 int32_t* neighbours_out, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Table utilities.

@@ -11,7 +11,7 @@ from . import build as _build
 
 _c = ctypes
 c_i32p = _c.c_void_p  # device pointers travel as integers
-MKE_ABI_VERSION = 3
+MKE_ABI_VERSION = 4
 MKE_EINVAL = -100000
 MKE_MAX_NEG = 32
 MKE_MAX_TRY = 10
@@ -109,6 +109,10 @@ SIGNATURES = {
     "mke_ipc_export": (_i32, [_vp, _c.c_char_p]),
     "mke_ipc_open": (_i32, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "mke_ipc_close": (_i32, [_vp]),
+    "mke_sim_rank_workspace_floats": (_c.c_int64, [_i32, _i32, _i32]),
+    "mke_sim_rank": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mke_sim_topk_workspace_floats": (_c.c_int64, [_i32, _i32, _i32]),
+    "mke_sim_topk": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _c.c_int64, _vp, _vp]),
     "mke_table_export": (_i32, [_PT, _vp, _i32, _vp, _vp]),
     "mke_fill_rows": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp]),
 }

@@ -42,8 +42,10 @@ def _triples(lst, with_weight=False):
 def _neighbour_matrix(neighbors, rows):
     """dict entity -> candidate list (base/batch.py:119-150) as an int32 [rows, k] matrix; entities
     without an entry get -1 in column 0 (fall back to the whole KG, neighbor.get(e, entities_list))."""
-    if not neighbors:
+    if neighbors is None or len(neighbors) == 0:
         return None
+    if hasattr(neighbors, "matrix"):  # refapi.base.batch.NeighbourTable: already on the device
+        return neighbors.matrix
     k = min(len(v) for v in neighbors.values())
     m = -np.ones((rows, k), dtype=np.int32)
     for e, cand in neighbors.items():

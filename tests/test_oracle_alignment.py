@@ -1,0 +1,40 @@
+"""oracle/alignment.py against the reference's own base/alignment.py and base/batch.py outputs
+(tests/golden/ref_sim.npz, generated in the build container by tests/golden/make_golden_sim.py)."""
+import numpy as np
+import pytest
+
+from oracle import alignment as oa
+
+
+@pytest.fixture(scope="module")
+def ref(golden):
+    return golden("ref_sim.npz")
+
+
+def test_greedy_alignment_matches_reference(ref):
+    top_k = ref["top_k"].tolist()
+    for c in range(len(ref["align_cases"])):
+        a, b = ref["align%d_a" % c], ref["align%d_b" % c]
+        rest, hits, mr, mrr = oa.greedy_alignment(a, b, top_k, normalize=True)
+        assert hits[0] == pytest.approx(float(ref["align%d_hits1" % c]))
+        assert np.array_equal(np.round(ref["align%d_hits" % c] / len(a) * 100, 3), hits)
+        assert mr == pytest.approx(float(ref["align%d_mr" % c]), rel=1e-12)
+        assert mrr == pytest.approx(float(ref["align%d_mrr" % c]), rel=1e-12)
+        top1 = np.array([j for _, j in sorted(rest)])
+        assert np.array_equal(top1, ref["align%d_top1" % c])
+
+
+def test_find_neighbours_matches_reference(ref):
+    for c, (n, d, k) in enumerate(ref["nb_cases"].tolist()):
+        got = oa.find_neighbours(ref["nb%d_ids" % c], ref["nb%d_e" % c], k)
+        want = ref["nb%d_lists" % c]
+        # the reference's list order is argpartition's; compare as sets (both sorted by id here)
+        assert np.array_equal(np.sort(got, axis=1), want)
+
+
+def test_stable_tie_rule():
+    s = np.array([[0.5, 0.9, 0.5, 0.5], [0.1, 0.1, 0.1, 0.1]], dtype=np.float32)
+    rank, top1 = oa.gold_ranks(s, gold=np.array([2, 3]))
+    assert rank.tolist() == [2, 3] and top1.tolist() == [1, 0]
+    rank, _ = oa.gold_ranks(s, gold=np.array([0, 0]))
+    assert rank.tolist() == [1, 0]

@@ -1,14 +1,9 @@
 #!/bin/bash
-# Phase-1 schedule sweep on one B200 (run under gpurun): parity tests first, then bench lines for the
-# one-wave kernel and the row-stream schedule under its knobs, then one ncu capture.
+# GPU session script (run under gpurun): parity tests, phase-1 schedule sweep, sim kernel timings.
 out=gpurun_out/sweep_$1
 mkdir -p $out
 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/pytest.log
-tail -5 $out/pytest.log
-run() {  # name, env..., -- args
-  name=$1; shift
-  env "$@" > /dev/null 2>&1 || true
-}
+tail -15 $out/pytest.log
 b() { name=$1; shift; ( "$@" ) > $out/$name.json 2> $out/$name.err; python - $out/$name.json $name <<'PY'
 import json,sys
 try:
@@ -21,16 +16,10 @@ PY
 B="python bench.py --no-cpu-baseline --steps 460 --warmup 46"
 b v0 $B --variant 0
 b v3 $B --variant 3
+b v3_b6 env MKE_Q8P_BLOCKS=6 $B --variant 3
 b v3_b4 env MKE_Q8P_BLOCKS=4 $B --variant 3
-b v3_b3 env MKE_Q8P_BLOCKS=3 $B --variant 3
-b v3_b5 env MKE_Q8P_BLOCKS=5 $B --variant 3
-b v3_cg env MKE_Q8_CFG=11 $B --variant 0
-b v3_d4 env MKE_Q8_CFG=12 $B --variant 0
-b v3_d4cg env MKE_Q8_CFG=13 $B --variant 0
-b v3_d4_b4 env MKE_Q8_CFG=12 MKE_Q8P_BLOCKS=4 $B --variant 0
-b v0_again $B --variant 0
+b v3_d4_b6 env MKE_Q8_CFG=12 MKE_Q8P_BLOCKS=6 $B --variant 0
 b v3_again $B --variant 3
-b big_v0 $B --variant 0 --workload synth1m_rel_d128_b20000_k25 --steps 200 --warmup 20
 b big_v3 $B --variant 3 --workload synth1m_rel_d128_b20000_k25 --steps 200 --warmup 20
-ncu --set full --clock-control none --import-source on -k regex:rel_fused_q8p -s 20 -c 2 -o $out/ncu_q8p python bench.py --no-cpu-baseline --steps 30 --warmup 5 --variant 3 > $out/ncu.log 2>&1
-ls -la $out
+python tools/bench_sim.py > $out/sim.json 2> $out/sim.err; cat $out/sim.json; tail -3 $out/sim.err
+ls $out
