@@ -32,7 +32,7 @@ constexpr int q8p_max_regs(int minb) {
   return r > 255 ? 248 : r;
 }
 
-template <int FPL, int D, int MINB, bool CG>
+template <int FPL, int D, int MINB, bool HOLD>
 __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) rel_fused_q8p_kernel(const RelStepParams p, const int passes) {
   constexpr int WARPS = kQ8pWarps;
   constexpr int stride = FPL * 8;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       if (iss_c == 0) __syncwarp();  // the id list of positive iss_n was landed by other lanes' copies
       const int32_t id = ids0[(iss_n & 1) * kIdStride + iss_c];
       const float* row = (iss_c == 1) ? p.rel_var + (size_t)id * stride : ent_var_row(p, id, stride);
-      stg.template issue<CG>(iss_slot, row, sub);
+      stg.issue(iss_slot, row, sub);
     }
     cp_async_commit();
     iss_slot = (iss_slot + 1 == D) ? 0 : iss_slot + 1;
@@ -115,6 +115,45 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
     float base[FPL], acc[FPL];
     float bb = 0.f;  // |base|^2
     {
+      float sp = 0.f;
+      if constexpr (!HOLD) {
+        // rows leave the ring one by one: each slot is refilled as soon as its row is in registers
+      float xh[FPL], xr[FPL], xt[FPL];
+      cp_async_wait<D - 1>();
+      stg.read(cons_slot, xh);
+      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      float sh = sumsq<FPL>(xh);
+      issue_next();
+      cp_async_wait<D - 1>();
+      stg.read(cons_slot, xr);
+      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      float sr = sumsq<FPL>(xr);
+      issue_next();
+      cp_async_wait<D - 1>();
+      stg.read(cons_slot, xt);
+      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      float st = sumsq<FPL>(xt);
+      issue_next();
+      qsum3(sh, sr, st);
+      const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
+      const float ir = p.rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
+      const float it = p.ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
+#pragma unroll
+      for (int k = 0; k < FPL; ++k) {
+        const float hh = xh[k] * ih, tt = xt[k] * it;
+        const float pd = fmaf(xr[k], ir, hh) - tt;  // pos_distance (losses.py:5)
+        sp = fmaf(pd, pd, sp);
+        acc[k] = pd;
+        // head side: nd = e^ + (r^ - t^) = e^ + (pd - h^);  tail side: nd = (h^ + r^) - e^ = (pd + t^) - e^
+        base[k] = side0 ? (pd - hh) : (pd + tt);
+        bb = fmaf(base[k], base[k], bb);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        sp += __shfl_xor_sync(kFull, sp, o);
+        bb += __shfl_xor_sync(kFull, bb, o);
+      }
+      } else {
       // the three rows stay in their ring slots and are read twice (norms first, then the
       // distance piece by piece): only base/acc and one piece of each row are ever live
       constexpr int NV4 = FPL / 4, REM = FPL % 4;
@@ -137,7 +176,6 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
       const float ir = p.rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
       const float it = p.ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
-      float sp = 0.f;
       auto piece = [&](int k, float xh, float xr, float xt) {
         const float hh = xh * ih, tt = xt * it;
         const float pd = fmaf(xr, ir, hh) - tt;  // pos_distance (losses.py:5)
@@ -173,6 +211,7 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       issue_next();
       issue_next();
       issue_next();
+      }
       float lpos, sg;
       softplus_sigmoid(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
       const float wgt = (p.w != nullptr && active ? __ldg(p.w + i) : 1.f) * p.pos_scale;
@@ -262,9 +301,9 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
 
 // Grid: b blocks per SM with b chosen so that the quarters (12 per block) divide the batch into
 // whole passes as evenly as possible; ties go to the larger b (more rows in flight).
-template <int FPL, int D, int MINB, bool CG>
+template <int FPL, int D, int MINB, bool HOLD>
 static int launch_q8p(const RelStepParams& p, cudaStream_t stream) {
-  auto kern = rel_fused_q8p_kernel<FPL, D, MINB, CG>;
+  auto kern = rel_fused_q8p_kernel<FPL, D, MINB, HOLD>;
   constexpr int per_block = kQ8pWarps * kQPerWarp;
   static int per_sm_cached = 0;
   if (per_sm_cached == 0) {
@@ -312,13 +351,13 @@ int launch_rel_q8p(const RelStepParams& p, int cfg, cudaStream_t stream) {
   const int R = 3 + p.K;
   const bool deep = 2 * 6 <= R, shallow = 2 * 4 <= R;
   if (!shallow) return 1;
-  const bool cg = (cfg & 1) != 0;
+  const bool hold = (cfg & 1) != 0;  // positive rows held in the ring and read twice (fewer registers)
   const bool d4 = (cfg & 2) != 0 || !deep;
   switch (p.stride) {
 #define MKE_Q8P_CASE(STRIDE, FPL, MINB)                                          \
   case STRIDE:                                                                   \
-    if (d4) return cg ? launch_q8p<FPL, 4, MINB, true>(p, stream) : launch_q8p<FPL, 4, MINB, false>(p, stream); \
-    return cg ? launch_q8p<FPL, 6, MINB, true>(p, stream) : launch_q8p<FPL, 6, MINB, false>(p, stream);
+    if (d4) return hold ? launch_q8p<FPL, 4, MINB, true>(p, stream) : launch_q8p<FPL, 4, MINB, false>(p, stream); \
+    return hold ? launch_q8p<FPL, 6, MINB, true>(p, stream) : launch_q8p<FPL, 6, MINB, false>(p, stream);
     MKE_Q8P_CASE(32, 4, 6)
     MKE_Q8P_CASE(64, 8, 6)
     MKE_Q8P_CASE(80, 10, 6)

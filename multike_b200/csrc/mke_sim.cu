@@ -264,14 +264,27 @@ __global__ void __launch_bounds__(kTopkThreads) row_topk_kernel(const float* __r
     const int nb = pass < 2 ? 2048 : 1024;
     for (int b = tid; b < nb; b += kTopkThreads) hist[b] = 0u;
     __syncthreads();
-    for (int c0 = 0; c0 < n2; c0 += kTopkThreads) {
-      const int c = c0 + tid;
-      bool ok = c < n2;
-      const uint32_t key = ok ? ord_key(s[c]) : 0u;
-      ok = ok && (key & mask) == prefix;
-      const unsigned bin = ok ? ((key >> shift) & (unsigned)(nb - 1)) : (0x10000u + (unsigned)lane);
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+    // four consecutive columns per thread and trip (rows are 16-byte aligned and padded to a
+    // multiple of four floats; the pad is masked).  Pass 0 sees every column and only a handful
+    // of distinct bins (the top bits of sims in [-1, 1]): one shared-memory atomic per warp and
+    // distinct bin (match.any).  Later passes see only the few columns of the threshold bin.
+    for (int c0 = 0; c0 < n2; c0 += 4 * kTopkThreads) {
+      const int c = c0 + 4 * tid;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < n2) v = *reinterpret_cast<const float4*>(s + c);
+      const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t key = ord_key(ve[e]);
+        const bool ok = c + e < n2 && (key & mask) == prefix;
+        const unsigned bin = (key >> shift) & (unsigned)(nb - 1);
+        if (pass == 0) {
+          const unsigned peers = __match_any_sync(0xffffffffu, ok ? bin : 0xffffffffu);
+          if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        } else if (ok) {
+          atomicAdd(&hist[bin], 1u);
+        }
+      }
     }
     __syncthreads();
     if (warp == 0) {

@@ -300,3 +300,54 @@ def test_literal_autoencoder_matches_oracle(tf32, tol, capsys):
     want_enc = o.encode(data)   # values of order 1e2 (N(0,1) weights): tolerance relative to the largest code
     np.testing.assert_allclose(enc, want_enc, rtol=0, atol=(1e-3 if tf32 else 1e-5) * np.abs(want_enc).max())
     assert set(m.weights) == {"encoder_h0", "encoder_h1", "encoder_h2", "decoder_h0", "decoder_h1", "decoder_h2"}
+
+
+def _hits1_lines(out, label):
+    """Hits@1 of every 'quick results' line that follows a '<label> ... results:' header"""
+    import re
+    vals, armed = [], False
+    for line in out.splitlines():
+        if line.endswith("results:"):
+            armed = line.startswith(label + " ")
+        elif armed and line.startswith("quick results"):
+            vals.append(float(re.search(r"=\s*\[\s*([0-9.]+)", line).group(1)))
+            armed = False
+    return vals
+
+
+def test_drivers_run_itc_and_ssl_schedules(capsys, tmp_path):
+    """refapi.MultiKE_CSL.MultiKE_CV.run (run_ITC.py) and refapi.MultiKE_Late.MultiKE_Late.run
+    (run_SSL.py) on a small synthetic three-view dataset: the whole schedule executes on the
+    device (views, cross-KG steps, soft predicate refresh, truncated neighbours, evaluation,
+    save), and alignment quality rises above the name view alone."""
+    import os
+    import multiview_fixture as mv
+    from multike_b200.refapi.MultiKE_CSL import MultiKE_CV
+    from multike_b200.refapi.MultiKE_Late import MultiKE_Late
+    data, args, pam = mv.make()
+    args.output = str(tmp_path) + "/"
+    model = MultiKE_CV(data, args, pam)
+    model.run()
+    out = capsys.readouterr().out
+    for needle in ("epoch 4 of rel. view", "epoch 4 of att. view", "cross-kg entity inference in rel. view",
+                   "cross-kg relation inference in rel. view", "cross-kg attribute inference in attr. view",
+                   "epoch 4 of common space learning", "neighbor dict: 400", "Embeddings saved!", "final test results:"):
+        assert needle in out, needle
+    assert [p for p, _ in pam.updates] == []  # refresh is due at epochs that are multiples of 10 only
+    nv, final = _hits1_lines(out, "nv"), _hits1_lines(out, "final")
+    assert nv[0] >= 55                             # ~60 % of the names are shared exactly
+    assert final[-1] >= nv[-1] - 10.0              # the combined space keeps (or beats) the name view
+    assert sorted(os.listdir(model.out_folder)) == ["attr_embeds.npy", "av_ent_embeds.npy", "ent_embeds.npy",
+                                                    "nv_ent_embeds.npy", "rel_embeds.npy", "rv_ent_embeds.npy"]
+    assert model._rv.kg1.neighbours is not None and model._rv.kg1.neighbours.shape == (800, 39)  # int((1 - 0.9) * 400) == 39
+    # SSL schedule
+    data, args, pam = mv.make(seed=1)
+    args.output = str(tmp_path) + "/"
+    late = MultiKE_Late(data, args, pam)
+    late.run()
+    out = capsys.readouterr().out
+    for needle in ("avg valid results:", "wvag valid results:", "weights ", "epoch 3 of shared space learning",
+                   "wvag test results:", "final test results:"):
+        assert needle in out, needle
+    assert [p for p, _ in pam.updates] == ["relation", "attribute"] * 2   # epochs 2 and 4
+    assert _hits1_lines(out, "avg")[-1] >= _hits1_lines(out, "nv")[0] - 10.0

@@ -26,6 +26,15 @@ def timed(fn, reps=5, warm=2):
 
 def main():
     d = 75
+    if "--profile" in sys.argv:  # one launch of each kernel for an ncu capture
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        a = torch.randn(10000, d, device="cuda", generator=gen)
+        b = torch.randn(70000, d, device="cuda", generator=gen)
+        S.sim_rank(a, b, normalize=True)
+        e = torch.randn(100000, d, device="cuda", generator=gen)
+        S.sim_topk(e / e.norm(dim=1, keepdim=True), 2000, chunk_rows=65536)
+        torch.cuda.synchronize()
+        return
     gen = torch.Generator(device="cuda").manual_seed(0)
     out = {}
     for name, n1, n2 in (("valid_10k_x_70k", 10000, 70000), ("test_60k_x_60k", 60000, 60000)):
