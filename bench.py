@@ -312,6 +312,16 @@ def main():
     p1_ms = tot.value / max(cnt.value, 1)
     _cabi.check(lib.mke_timing_enable(0))
 
+    # how much of a CUDA-event pair is not the kernel: the same pair around a one-row fill kernel
+    probe = torch.zeros(8, device="cuda")
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+    for a, b in pairs:
+        a.record()
+        _cabi.check(lib.mke_fill_rows(probe.data_ptr(), 1, 8, 8, 0.0, _cabi.current_stream()))
+        b.record()
+    torch.cuda.synchronize()
+    event_floor_ms = sorted(a.elapsed_time(b) for a, b in pairs)[len(pairs) // 2]
+
     # ---- end-to-end leg: every step copies its positives in from pinned HOST memory and its
     # loss back out (mke_rel_view_t.host_triples / host_step_loss); one sync at the end --------
     rv.use_host_triples()
@@ -365,7 +375,10 @@ def main():
                          "traffic_note": "dram bytes per launch, ncu --set full (cold L2), profiles/r1_traffic.json",
                          "algorithmic_bytes": alg_bytes, "kernel": P1_KERNEL[args.variant] + " (phase 1)",
                          "peak_source": peak_kind, "launch_ms": p1_ms,
-                         "bytes_per_positive": bytes_per_positive(dim, K)},
+                         "bytes_per_positive": bytes_per_positive(dim, K),
+                         "event_pair_floor_ms": event_floor_ms,
+                         "event_pair_floor_note": "median of the same CUDA-event pair around a one-row fill kernel: "
+                                                  "the part of launch_ms that is launch/event latency, not kernel"},
         }
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_baseline_run(args.workload, args.cpu_steps, 1)

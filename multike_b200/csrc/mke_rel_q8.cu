@@ -274,7 +274,7 @@ int launch_rel_q8(const RelStepParams& p, cudaStream_t stream) {
   // <floats per lane, threads per block, min blocks per SM, TMA bulk-reduce scatter>.  The defaults
   // come from the sweep in profiles/r1_phase1_tuning.md: fewer, fatter blocks (more registers, no
   // spills) beat maximum occupancy because the kernel is bound by row traffic, not by issue.
-  // 10..13: persistent row-stream schedule (mke_rel_q8p.cu): bit0 = positive rows held in the ring, bit1 = ring of 4
+  // 10..13: persistent row-stream schedule (mke_rel_q8p.cu): bit0 = build without a register cap, bit1 = ring of 4
   if (cfg >= 10 && cfg <= 13) {
     const int rc = launch_rel_q8p(p, cfg - 10, stream);
     if (rc != 1) return rc;  // 1 = launch shape not covered there

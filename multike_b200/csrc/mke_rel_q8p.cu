@@ -32,10 +32,43 @@ constexpr int q8p_max_regs(int minb) {
   return r > 255 ? 248 : r;
 }
 
-template <int FPL, int D, int MINB, bool HOLD>
+// MUFU forms without the denormal / range guards of rsqrtf, __expf and __logf: every argument here is
+// >= 1e-12 (clamped sums of squares) or in [-9, 9] (squared distances of unit rows), so the .ftz
+// forms are exact replacements and save ~12 instructions per row.
+__device__ __forceinline__ float mufu_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log(1 + exp(x)) and sigmoid(x) as the reference writes them (losses.py:9-10), cf. softplus_sigmoid
+__device__ __forceinline__ void softplus_sigmoid_mufu(float x, float& sp, float& sg) {
+  const float ex = mufu_ex2(x * 1.4426950408889634f);
+  const float one_p = 1.0f + ex;
+  sp = mufu_lg2(one_p) * 0.6931471805599453f;
+  sg = ex * mufu_rcp(one_p);
+}
+
+template <int FPL, int D, int MINB, bool SHARDED>
 __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) rel_fused_q8p_kernel(const RelStepParams p, const int passes) {
   constexpr int WARPS = kQ8pWarps;
   constexpr int stride = FPL * 8;
+  constexpr int H = FPL / 2;           // packed fp32 pairs per lane (fma.rn.f32x2: one issue slot, two FMAs)
+  constexpr bool ODD = (FPL & 1) != 0;  // + one scalar tail element
   using Ring = Stage<FPL, D>;
   __shared__ __align__(128) unsigned char s_ring[WARPS][Ring::kBytes];
   __shared__ int32_t s_ids[WARPS][kQPerWarp][2][kIdStride];
@@ -47,10 +80,6 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
   Ring stg;
   stg.base = (uint32_t)__cvta_generic_to_shared(&s_ring[wib][0]);
   stg.lane = lane;
-  RowScatter<FPL, false> out;
-  out.buf = 0;
-  out.qmask = 0xffu << (lane & 24);
-  out.sub = sub;
   volatile int32_t* const ids0 = s_ids[wib][q][0];
   const uint32_t ids_base = (uint32_t)__cvta_generic_to_shared(&s_ids[wib][q][0][0]);
   const int total = p.len1 + p.len2;
@@ -60,6 +89,32 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
   const int g = (blockIdx.x * WARPS + wib) * kQPerWarp + q;
   float* const rel_grad = rel_grad_replica(p);
   float loss_local = 0.f;
+
+  // entity rows: one local table, or the owner's shard through its peer mapping (compile-time choice)
+  auto evar = [&](int32_t id) -> const float* {
+    if constexpr (!SHARDED) return p.ent_var + (size_t)id * stride;
+    int s;
+    int32_t l;
+    p.smap.locate(id, s, l);
+    return p.sh.var[s] + (size_t)l * stride;
+  };
+  auto egrad = [&](int32_t id) -> float* {
+    if constexpr (!SHARDED) return p.ent_grad + (size_t)id * stride;
+    int s;
+    int32_t l;
+    p.smap.locate(id, s, l);
+    return p.sh.grad[s] + (size_t)l * stride;
+  };
+  auto emark = [&](int32_t id) {
+    if constexpr (!SHARDED) {
+      mark_touched(p.ent_touched, id);
+    } else {
+      int s;
+      int32_t l;
+      p.smap.locate(id, s, l);
+      mark_touched(p.sh.touched[s], l);
+    }
+  };
 
   // id list of positive i -> buffer `buf`, asynchronously (the copies join the next commit group)
   auto ids_issue = [&](int buf, int i) {
@@ -78,20 +133,26 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
   };
 
   // producer side of the row stream
-  int iss_n = 0, iss_c = 0, iss_slot = 0, cons_slot = 0;
+  // One ring position serves both sides: take() reads the oldest slot, issue_next() refills that
+  // very slot with the row D positions further down the stream and moves on.
+  int iss_n = 0, iss_c = 0, slot = 0;
   auto issue_next = [&]() {
     if (iss_n < passes) {
       if (iss_c == 0) __syncwarp();  // the id list of positive iss_n was landed by other lanes' copies
       const int32_t id = ids0[(iss_n & 1) * kIdStride + iss_c];
-      const float* row = (iss_c == 1) ? p.rel_var + (size_t)id * stride : ent_var_row(p, id, stride);
-      stg.issue(iss_slot, row, sub);
+      const float* row = (iss_c == 1) ? p.rel_var + (size_t)id * stride : evar(id);
+      stg.issue(slot, row, sub);
     }
     cp_async_commit();
-    iss_slot = (iss_slot + 1 == D) ? 0 : iss_slot + 1;
+    slot = (slot + 1 == D) ? 0 : slot + 1;
     if (++iss_c == R) {
       iss_c = 0;
       ++iss_n;
     }
+  };
+  auto take = [&](float (&x)[FPL]) {  // oldest row of the ring -> registers
+    cp_async_wait<D - 1>();
+    stg.read(slot, x);
   };
 
   ids_issue(0, g);
@@ -112,130 +173,81 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
     // ---- positive term ---------------------------------------------------------------------
     const bool side0 = (side & 1u) != 0u;  // side of negative 0: true = head replaced
     const float sgn = side0 ? 1.f : -1.f;
-    float base[FPL], acc[FPL];
+    // base = the part of a same-side negative's distance that does not depend on the negative;
+    // accs = sgn * (d loss / d pos_distance + sum over negatives of d loss / d neg_distance): kept
+    // pre-multiplied by sgn so that a negative costs one packed multiply and one packed add
+    float2 base2[H > 0 ? H : 1], accs2[H > 0 ? H : 1];
+    float base_t = 0.f, accs_t = 0.f;
     float bb = 0.f;  // |base|^2
     {
-      float sp = 0.f;
-      if constexpr (!HOLD) {
-        // rows leave the ring one by one: each slot is refilled as soon as its row is in registers
       float xh[FPL], xr[FPL], xt[FPL];
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, xh);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      take(xh);
       float sh = sumsq<FPL>(xh);
       issue_next();
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, xr);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      take(xr);
       float sr = sumsq<FPL>(xr);
       issue_next();
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, xt);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      take(xt);
       float st = sumsq<FPL>(xt);
       issue_next();
       qsum3(sh, sr, st);
-      const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
-      const float ir = p.rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
-      const float it = p.ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
+      const float ih = p.ent_norm ? mufu_rsqrt(fmaxf(sh, kNormEps)) : 1.f;
+      const float ir = p.rel_norm ? mufu_rsqrt(fmaxf(sr, kNormEps)) : 1.f;
+      const float it = p.ent_norm ? mufu_rsqrt(fmaxf(st, kNormEps)) : 1.f;
+      float pd[FPL], bs[FPL];
+      float sp = 0.f;
 #pragma unroll
       for (int k = 0; k < FPL; ++k) {
         const float hh = xh[k] * ih, tt = xt[k] * it;
-        const float pd = fmaf(xr[k], ir, hh) - tt;  // pos_distance (losses.py:5)
-        sp = fmaf(pd, pd, sp);
-        acc[k] = pd;
+        pd[k] = fmaf(xr[k], ir, hh) - tt;  // pos_distance (losses.py:5)
+        sp = fmaf(pd[k], pd[k], sp);
         // head side: nd = e^ + (r^ - t^) = e^ + (pd - h^);  tail side: nd = (h^ + r^) - e^ = (pd + t^) - e^
-        base[k] = side0 ? (pd - hh) : (pd + tt);
-        bb = fmaf(base[k], base[k], bb);
+        bs[k] = side0 ? (pd[k] - hh) : (pd[k] + tt);
+        bb = fmaf(bs[k], bs[k], bb);
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
         sp += __shfl_xor_sync(kFull, sp, o);
         bb += __shfl_xor_sync(kFull, bb, o);
-      }
-      } else {
-      // the three rows stay in their ring slots and are read twice (norms first, then the
-      // distance piece by piece): only base/acc and one piece of each row are ever live
-      constexpr int NV4 = FPL / 4, REM = FPL % 4;
-      cp_async_wait<D - 3>();
-      const int s0 = cons_slot;
-      const int s1 = (s0 + 1 == D) ? 0 : s0 + 1;
-      const int s2 = (s1 + 1 == D) ? 0 : s1 + 1;
-      cons_slot = (s2 + 1 == D) ? 0 : s2 + 1;
-      float sh, sr, st;
-      {
-        float x[FPL];
-        stg.read(s0, x);
-        sh = sumsq<FPL>(x);
-        stg.read(s1, x);
-        sr = sumsq<FPL>(x);
-        stg.read(s2, x);
-        st = sumsq<FPL>(x);
-      }
-      qsum3(sh, sr, st);
-      const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
-      const float ir = p.rel_norm ? rsqrtf(fmaxf(sr, kNormEps)) : 1.f;
-      const float it = p.ent_norm ? rsqrtf(fmaxf(st, kNormEps)) : 1.f;
-      auto piece = [&](int k, float xh, float xr, float xt) {
-        const float hh = xh * ih, tt = xt * it;
-        const float pd = fmaf(xr, ir, hh) - tt;  // pos_distance (losses.py:5)
-        sp = fmaf(pd, pd, sp);
-        acc[k] = pd;
-        // head side: nd = e^ + (r^ - t^) = e^ + (pd - h^);  tail side: nd = (h^ + r^) - e^ = (pd + t^) - e^
-        base[k] = side0 ? (pd - hh) : (pd + tt);
-        bb = fmaf(base[k], base[k], bb);
-      };
-#pragma unroll
-      for (int c = 0; c < NV4; ++c) {
-        float vh[4], vr[4], vt[4];
-        stg.read4(s0, c, vh);
-        stg.read4(s1, c, vr);
-        stg.read4(s2, c, vt);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) piece(4 * c + k, vh[k], vr[k], vt[k]);
-      }
-      if constexpr (REM > 0) {
-        float vh[REM], vr[REM], vt[REM];
-        stg.read_tail(s0, vh);
-        stg.read_tail(s1, vr);
-        stg.read_tail(s2, vt);
-#pragma unroll
-        for (int k = 0; k < REM; ++k) piece(4 * NV4 + k, vh[k], vr[k], vt[k]);
-      }
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        sp += __shfl_xor_sync(kFull, sp, o);
-        bb += __shfl_xor_sync(kFull, bb, o);
-      }
-      // the three slots are free: the stream moves on by three rows
-      issue_next();
-      issue_next();
-      issue_next();
       }
       float lpos, sg;
-      softplus_sigmoid(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
+      softplus_sigmoid_mufu(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
       const float wgt = (p.w != nullptr && active ? __ldg(p.w + i) : 1.f) * p.pos_scale;
       if (active) loss_local += wgt * lpos;
-      const float cp = 2.f * sg * wgt;
+      const float cps = 2.f * sg * wgt * sgn;
+      float first[FPL];  // sgn * d loss / d pos_distance
 #pragma unroll
-      for (int k = 0; k < FPL; ++k) acc[k] *= cp;  // d loss / d pd; the K-loop adds the negatives
+      for (int k = 0; k < FPL; ++k) first[k] = pd[k] * cps;
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        base2[k] = make_float2(bs[2 * k], bs[2 * k + 1]);
+        accs2[k] = make_float2(first[2 * k], first[2 * k + 1]);
+      }
+      if constexpr (ODD) {
+        base_t = bs[FPL - 1];
+        accs_t = first[FPL - 1];
+      }
       // the endpoint that no same-side negative shares gets its positive-term gradient now
-      if (active) out.add(ent_grad_row(p, side0 ? h : t, stride), acc, sgn);
+      if (active) red_row<FPL>(egrad(side0 ? h : t), sub, first, 1.f);
     }
     // ---- negatives ---------------------------------------------------------------------------
 #pragma unroll 1
     for (int j = 0; j < K; ++j) {
       float x[FPL];
-      cp_async_wait<D - 1>();
-      stg.read(cons_slot, x);
-      cons_slot = (cons_slot + 1 == D) ? 0 : cons_slot + 1;
+      take(x);
       const int32_t e = ids[3 + j];
       // |nd|^2 = |base + s ie e|^2 = |base|^2 + 2 s ie (base.e) + ie^2 (e.e)
-      float ee = 0.f, be = 0.f;
+      float2 ee2 = make_float2(0.f, 0.f), be2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < FPL; ++k) {
-        ee = fmaf(x[k], x[k], ee);
-        be = fmaf(x[k], base[k], be);
+      for (int k = 0; k < H; ++k) {
+        const float2 xv = make_float2(x[2 * k], x[2 * k + 1]);
+        ee2 = __ffma2_rn(xv, xv, ee2);
+        be2 = __ffma2_rn(xv, base2[k], be2);
+      }
+      float ee = ee2.x + ee2.y, be = be2.x + be2.y;
+      if constexpr (ODD) {
+        ee = fmaf(x[FPL - 1], x[FPL - 1], ee);
+        be = fmaf(x[FPL - 1], base_t, be);
       }
       issue_next();  // the slot is free: the sums above consumed x
 #pragma unroll
@@ -243,44 +255,58 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
         ee += __shfl_xor_sync(kFull, ee, o);
         be += __shfl_xor_sync(kFull, be, o);
       }
-      const float ie = p.ent_norm ? rsqrtf(fmaxf(ee, kNormEps)) : 1.f;
+      const float ie = p.ent_norm ? mufu_rsqrt(fmaxf(ee, kNormEps)) : 1.f;
       const float sie = sgn * ie;
       const float sn = fmaf(ie * ie, ee, fmaf(2.f * sie, be, bb));  // -neg_score (losses.py:8)
       float lneg, sg;
-      softplus_sigmoid(-sn, lneg, sg);  // log(1 + exp(neg_score)), neg_score = -sn
+      softplus_sigmoid_mufu(-sn, lneg, sg);  // log(1 + exp(neg_score)), neg_score = -sn
       const bool odd = (((side >> j) & 1u) != 0u) != side0;
       const bool on = active && !odd;
-      const float cn = on ? -2.f * sg : 0.f;
+      const float cs = on ? -2.f * sg * sgn : 0.f;  // sgn * d loss / d |nd|^2 * 2
       if (on) loss_local += lneg;
+      const float2 sie2 = make_float2(sie, sie), cs2 = make_float2(cs, cs);
+      float y[FPL];  // sgn * d loss / d neg_distance = the gradient row of the corrupted entity
 #pragma unroll
-      for (int k = 0; k < FPL; ++k) {
-        x[k] = fmaf(x[k], sie, base[k]);  // neg_distance (losses.py:6)
-        acc[k] = fmaf(cn, x[k], acc[k]);
+      for (int k = 0; k < H; ++k) {
+        const float2 nd = __ffma2_rn(make_float2(x[2 * k], x[2 * k + 1]), sie2, base2[k]);  // neg_distance (losses.py:6)
+        const float2 yy = __fmul2_rn(nd, cs2);
+        accs2[k] = __fadd2_rn(accs2[k], yy);
+        y[2 * k] = yy.x;
+        y[2 * k + 1] = yy.y;
       }
-      if (on) out.add(ent_grad_row(p, e, stride), x, cn * sgn);
+      if constexpr (ODD) {
+        y[FPL - 1] = fmaf(x[FPL - 1], sie, base_t) * cs;
+        accs_t += y[FPL - 1];
+      }
+      if (on) red_row<FPL>(egrad(e), sub, y, 1.f);
     }
     // ---- r gets every same-side term, the shared endpoint likewise ---------------------------
     if (active) {
-      out.add(rel_grad + (size_t)r * stride, acc, 1.f);
-      out.add(ent_grad_row(p, side0 ? t : h, stride), acc, -sgn);
-      for (int c = sub; c < K; c += 8) ent_mark(p, ids[3 + c]);
+      float a[FPL];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        a[2 * k] = accs2[k].x;
+        a[2 * k + 1] = accs2[k].y;
+      }
+      if constexpr (ODD) a[FPL - 1] = accs_t;
+      red_row<FPL>(rel_grad + (size_t)r * stride, sub, a, sgn);
+      red_row<FPL>(egrad(side0 ? t : h), sub, a, -1.f);
+      for (int c = sub; c < K; c += 8) emark(ids[3 + c]);
       if (sub == 0) {
-        ent_mark(p, h);
-        ent_mark(p, t);
+        emark(h);
+        emark(t);
         mark_touched(p.rel_touched, r);
       }
     }
-    // ---- negatives on the other side than negative 0 (rare), once base/acc are dead ----------
+    // ---- negatives on the other side than negative 0 (rare), once base/accs are dead ---------
     const bool mixed = active && side != 0u && side != low_ones(K);
     if (__any_sync(kFull, mixed)) {
       for (int j = 1; j < K; ++j) {
         const bool odd = active && ((((side >> j) & 1u) != 0u) != side0);
         if (__any_sync(kFull, odd))
-          loss_local += odd_negative<FPL>(
-              ent_var_row(p, h, stride), p.rel_var + (size_t)r * stride, ent_var_row(p, t, stride),
-              ent_var_row(p, ids[3 + j], stride), ent_grad_row(p, h, stride), rel_grad + (size_t)r * stride,
-              ent_grad_row(p, t, stride), ent_grad_row(p, ids[3 + j], stride), p.ent_norm, p.rel_norm, !side0, odd,
-              sub);
+          loss_local += odd_negative<FPL>(evar(h), p.rel_var + (size_t)r * stride, evar(t), evar(ids[3 + j]), egrad(h),
+                                          rel_grad + (size_t)r * stride, egrad(t), egrad(ids[3 + j]), p.ent_norm,
+                                          p.rel_norm, !side0, odd, sub);
       }
     }
     __syncwarp();  // this positive's id buffer is rewritten two positives from now
@@ -301,9 +327,9 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
 
 // Grid: b blocks per SM with b chosen so that the quarters (12 per block) divide the batch into
 // whole passes as evenly as possible; ties go to the larger b (more rows in flight).
-template <int FPL, int D, int MINB, bool HOLD>
+template <int FPL, int D, int MINB, bool SHARDED>
 static int launch_q8p(const RelStepParams& p, cudaStream_t stream) {
-  auto kern = rel_fused_q8p_kernel<FPL, D, MINB, HOLD>;
+  auto kern = rel_fused_q8p_kernel<FPL, D, MINB, SHARDED>;
   constexpr int per_block = kQ8pWarps * kQPerWarp;
   static int per_sm_cached = 0;
   if (per_sm_cached == 0) {
@@ -351,13 +377,15 @@ int launch_rel_q8p(const RelStepParams& p, int cfg, cudaStream_t stream) {
   const int R = 3 + p.K;
   const bool deep = 2 * 6 <= R, shallow = 2 * 4 <= R;
   if (!shallow) return 1;
-  const bool hold = (cfg & 1) != 0;  // positive rows held in the ring and read twice (fewer registers)
   const bool d4 = (cfg & 2) != 0 || !deep;
+  const bool roomy = (cfg & 1) != 0;  // experiment: 4 blocks per SM at most, no register cap to speak of
+  const bool sh = p.sharded != 0;
   switch (p.stride) {
-#define MKE_Q8P_CASE(STRIDE, FPL, MINB)                                          \
-  case STRIDE:                                                                   \
-    if (d4) return hold ? launch_q8p<FPL, 4, MINB, true>(p, stream) : launch_q8p<FPL, 4, MINB, false>(p, stream); \
-    return hold ? launch_q8p<FPL, 6, MINB, true>(p, stream) : launch_q8p<FPL, 6, MINB, false>(p, stream);
+#define MKE_Q8P_CASE(STRIDE, FPL, MINB)                                                                         \
+  case STRIDE:                                                                                                  \
+    if (roomy && !sh) return launch_q8p<FPL, 6, 4, false>(p, stream);                                           \
+    if (d4) return sh ? launch_q8p<FPL, 4, MINB, true>(p, stream) : launch_q8p<FPL, 4, MINB, false>(p, stream); \
+    return sh ? launch_q8p<FPL, 6, MINB, true>(p, stream) : launch_q8p<FPL, 6, MINB, false>(p, stream);
     MKE_Q8P_CASE(32, 4, 6)
     MKE_Q8P_CASE(64, 8, 6)
     MKE_Q8P_CASE(80, 10, 6)
