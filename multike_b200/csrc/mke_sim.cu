@@ -12,9 +12,9 @@
 // The contraction is 75..128 deep and has to order near-ties like the reference's fp32 sgemm, so
 // it runs on the fp32 FMA pipe (no tensor cores: tf32/bf16 would reorder the ranks): one thread
 // block owns a 128-row tile of A, streams 128-row tiles of B through a double-buffered cp.async
-// stage and keeps an 8 x 8 block of sims per thread in registers.  Every sim is one fmaf chain in
-// ascending k -- the same chain sim_gold_kernel uses -- so equal rows give bit-equal sims and the
-// tie rules below are exact.
+// stage and keeps an 8 x 8 block of sims per thread in registers.  Every sim is the sum of two fmaf
+// chains in ascending k (even and odd columns, packed FFMA2) -- the same two chains
+// sim_gold_kernel uses -- so equal rows give bit-equal sims and the tie rules below are exact.
 #include "mke_common.cuh"
 
 namespace mke {
@@ -60,10 +60,14 @@ __global__ void sim_gold_kernel(const float* __restrict__ a, const float* __rest
   const int g = gold ? __ldg(gold + i) : i;
   float acc = __int_as_float(0x7f800000);  // gold outside [0, n2): nothing ranks before it
   if (g >= 0 && g < n2) {
-    acc = 0.f;
     const float* x = a + (size_t)i * ws;
     const float* y = b + (size_t)g * ws;
-    for (int k = 0; k < ws; ++k) acc = fmaf(__ldg(x + k), __ldg(y + k), acc);
+    float even = 0.f, odd = 0.f;  // the two chains of the tile kernel's packed accumulators
+    for (int k = 0; k < ws; k += 2) {
+      even = fmaf(__ldg(x + k), __ldg(y + k), even);
+      odd = fmaf(__ldg(x + k + 1), __ldg(y + k + 1), odd);
+    }
+    acc = even + odd;
   }
   gold_score[i] = acc;
   rank[i] = 0;
@@ -156,12 +160,15 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
     __syncthreads();
     const float* At = As + ty * pitch;
     const float* Bt = Bs0 + (size_t)buf * kSimTile * pitch + tx * pitch;
-    float acc[8][8];
+    // Packed fp32 (fma.rn.f32x2, SASS FFMA2): every sim is accumulated as two chains -- the even
+    // and the odd columns of the embedding -- that ride in one 64-bit register pair and are added
+    // at the end; one issue slot feeds two FMAs, which is what lifts the scalar-FFMA issue limit.
+    float2 acc2[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
+      for (int j = 0; j < 8; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 1
     for (int k4 = 0; k4 < (p.ws >> 2); ++k4) {
       float4 a[8];
 #pragma unroll
@@ -169,17 +176,21 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = *reinterpret_cast<const float4*>(Bt + 16 * j * pitch + 4 * k4);
+        const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float v = acc[i][j];
-          v = fmaf(a[i].x, b.x, v);
-          v = fmaf(a[i].y, b.y, v);
-          v = fmaf(a[i].z, b.z, v);
-          v = fmaf(a[i].w, b.w, v);
-          acc[i][j] = v;
+          float2 v = acc2[i][j];
+          v = __ffma2_rn(make_float2(a[i].x, a[i].y), b01, v);
+          v = __ffma2_rn(make_float2(a[i].z, a[i].w), b23, v);
+          acc2[i][j] = v;
         }
       }
     }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
     // ---- epilogue of this tile ----------------------------------------------------------------
     const int col0 = jt * kSimTile + tx;
     if constexpr (RANK) {
