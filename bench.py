@@ -222,8 +222,10 @@ def run_sharded(args, rank, world, local_rank):
                        "steps_per_epoch": spe, "variant": "q8_ldg_red",
                        "l2": "no flush: per-rank working set exceeds L2 / rows come over NVLink",
                        "parallelism": "entity table row-sharded over %d GPUs, KG-block placement (each KG on half of "
-                                      "the ranks, positives trained where their rows live; peer gathers + peer "
-                                      "reductions inside phase 1), relation gradients NCCL all-reduced" % world},
+                                      "the ranks; %s; peer gathers + peer reductions inside phase 1), relation "
+                                      "gradients NCCL all-reduced" % (
+                                          world, "negatives scored on the rank that owns them, endpoint rows over NVLink"
+                                          if sv.owner_negs else "positives trained where their rows live")},
             "clocks": clk,
             # the multi-GPU driver keeps the triple lists resident; the host-fed path is the N=1 line
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MKE_ABI_VERSION 4
+#define MKE_ABI_VERSION 5
 #define MKE_EINVAL (-100000)
 #define MKE_MAX_NEG 32        /* K (negatives per positive) supported by the fused kernel */
 #define MKE_MAX_TRY 10        /* base/batch.py:86 max_try=10 */
@@ -365,6 +365,27 @@ int mke_sample_attribute_heads(const int32_t* pos1, int32_t len1, const mke_kg_s
                                const int32_t* pos2, int32_t len2, const mke_kg_sampler_t* kg2,
                                int32_t K, uint64_t seed, uint64_t step, int32_t index_base,
                                int32_t* neg_head, mke_stream_t stream);
+
+/*
+ * "Negatives where they live", for row-sharded entity tables: every rank
+ * of a KG's group walks ALL positives of the group's batch but scores only the negatives whose
+ * corrupted entity it owns -- the K rows that dominate a positive's traffic never cross NVLink;
+ * what still does are the two endpoint rows of a positive (when another rank owns them).
+ *
+ * mke_neg_keep_owned rewrites a sampled batch for one rank: negatives owned by other shards are
+ * replaced by `dummy_id` (a row of this shard) and their bit in neg_valid[i] is cleared.
+ * mke_rel_step_structured3 is mke_rel_step_structured2 with that mask and with the range
+ * [pos_own_lo, pos_own_hi) of positives whose POSITIVE term (losses.py:7) belongs to this launch;
+ * summed over the ranks of the group the gradients and the loss equal one full step.
+ */
+int mke_neg_keep_owned(int32_t* neg_ent, int32_t n, int32_t K, int32_t n_shards, int32_t shard_split,
+                       int32_t my_shard, int32_t dummy_id, uint32_t* neg_valid, mke_stream_t stream);
+int mke_rel_step_structured3(const mke_table_t* ent, const mke_table_t* rel,
+                             const int32_t* pos1, int32_t len1, const int32_t* pos2, int32_t len2,
+                             int32_t K, const int32_t* neg_ent, const uint32_t* neg_side,
+                             const uint32_t* neg_valid_or_null, int32_t pos_own_lo, int32_t pos_own_hi,
+                             const float* w_or_null, float pos_scale,
+                             double* loss_accum, int32_t variant, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Peer memory for row-sharded tables (one process per GPU; handles travel over torch.distributed).

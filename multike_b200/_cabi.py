@@ -11,7 +11,7 @@ from . import build as _build
 
 _c = ctypes
 c_i32p = _c.c_void_p  # device pointers travel as integers
-MKE_ABI_VERSION = 4
+MKE_ABI_VERSION = 5
 MKE_EINVAL = -100000
 MKE_MAX_NEG = 32
 MKE_MAX_TRY = 10
@@ -86,6 +86,9 @@ SIGNATURES = {
                                     _f32, _vp, _vp, _i32, _vp]),
     "mke_rel_step_structured": (_i32, [_PT, _PT, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
     "mke_rel_step_structured2": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp]),
+    "mke_rel_step_structured3": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp,
+                                        _i32, _vp]),
+    "mke_neg_keep_owned": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
     "mke_attr_cnn_param_count": (_c.c_int64, [_i32]),
     "mke_attr_cnn_workspace_floats": (_c.c_int64, [_i32, _i32]),

@@ -527,6 +527,8 @@ static int launch_rel(RelStepParams& p, int variant, cudaStream_t stream) {
     if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = no instantiation for this stride
   }
   MKE_CHECK_ARG(!p.sharded, "row-sharded entity tables need the quarter-warp kernel (variant 0, stride 32/64/80/104/128)");
+  MKE_CHECK_ARG(p.neg_valid == nullptr && p.pos_own_lo <= 0 && p.pos_own_hi >= n,
+                "ownership masks need the quarter-warp kernels (variant 0 or 3, stride 32/64/80/104/128)");
   if (variant == 1) {
     const size_t smem = (size_t)kTmaWarps * 4 * (3 + p.K) * p.stride * sizeof(float);
     if (smem <= 200 * 1024) {
@@ -598,6 +600,8 @@ extern "C" int mke_rel_step_sampled(const mke_table_t* ent, const mke_table_t* r
   MKE_CHECK_ARG(len2 == 0 || (pos2 && (K == 0 || kg2)), "kg2 slice needs positives and a sampler");
   MKE_CHECK_ARG(loss_accum, "loss_accum is null");
   RelStepParams p{};
+  p.pos_own_lo = 0;
+  p.pos_own_hi = 0x7fffffff;
   fill_tables(p, ent, rel);
   p.pos1 = pos1;
   p.len1 = len1;
@@ -630,7 +634,19 @@ extern "C" int mke_rel_step_structured2(const mke_table_t* ent, const mke_table_
                                         const uint32_t* neg_side, const float* w_or_null,
                                         float pos_scale, double* loss_accum, int32_t variant,
                                         mke_stream_t stream) {
+  return mke_rel_step_structured3(ent, rel, pos1, len1, pos2, len2, K, neg_ent, neg_side, nullptr, 0, 0x7fffffff,
+                                  w_or_null, pos_scale, loss_accum, variant, stream);
+}
+
+extern "C" int mke_rel_step_structured3(const mke_table_t* ent, const mke_table_t* rel,
+                                        const int32_t* pos1, int32_t len1, const int32_t* pos2,
+                                        int32_t len2, int32_t K, const int32_t* neg_ent,
+                                        const uint32_t* neg_side, const uint32_t* neg_valid_or_null,
+                                        int32_t pos_own_lo, int32_t pos_own_hi, const float* w_or_null,
+                                        float pos_scale, double* loss_accum, int32_t variant,
+                                        mke_stream_t stream) {
   if (int rc = validate_tables(ent, rel)) return rc;
+  MKE_CHECK_ARG(pos_own_lo >= 0 && pos_own_hi >= pos_own_lo, "bad owner range [%d, %d)", pos_own_lo, pos_own_hi);
   MKE_CHECK_ARG(K >= 0 && K <= MKE_MAX_NEG, "K=%d outside [0,%d]", K, MKE_MAX_NEG);
   MKE_CHECK_ARG(len1 >= 0 && len2 >= 0, "negative batch length");
   MKE_CHECK_ARG((uint64_t)len1 + (uint64_t)len2 < (1ull << 31), "batch too large");
@@ -638,6 +654,8 @@ extern "C" int mke_rel_step_structured2(const mke_table_t* ent, const mke_table_
   MKE_CHECK_ARG(K == 0 || len1 + len2 == 0 || (neg_ent && neg_side), "neg_ent/neg_side are null");
   MKE_CHECK_ARG(loss_accum, "loss_accum is null");
   RelStepParams p{};
+  p.pos_own_lo = 0;
+  p.pos_own_hi = 0x7fffffff;
   fill_tables(p, ent, rel);
   p.pos1 = pos1;
   p.len1 = len1;
@@ -647,6 +665,9 @@ extern "C" int mke_rel_step_structured2(const mke_table_t* ent, const mke_table_
   p.sampled = 0;
   p.neg_ent = neg_ent;
   p.neg_side = neg_side;
+  p.neg_valid = neg_valid_or_null;
+  p.pos_own_lo = pos_own_lo;
+  p.pos_own_hi = pos_own_hi;
   p.w = w_or_null;
   p.pos_scale = pos_scale;
   p.loss = loss_accum;

@@ -35,6 +35,12 @@ struct RelStepParams {
   uint64_t skey;
   const int32_t* neg_ent;
   const uint32_t* neg_side;
+  // "negatives where they live" (row-sharded tables, sharded.py): bit j of neg_valid[i] clear =>
+  // negative j of positive i belongs to another rank (its slot holds a local dummy row and
+  // contributes nothing); the positive term of positive i is this launch's only if
+  // pos_own_lo <= i < pos_own_hi.  NULL / [0, INT_MAX) => everything is this launch's.
+  const uint32_t* neg_valid;
+  int pos_own_lo, pos_own_hi;
   const float* w;
   float pos_scale;
   double* loss;

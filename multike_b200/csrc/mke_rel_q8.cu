@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
     }
     {
       uint32_t side = 0u;
+      uint32_t mine = 0xffffffffu;  // negatives of this positive that are this launch's (RelStepParams.neg_valid)
       const bool active = valid;
+      const bool pos_on = valid && i >= p.pos_own_lo && i < p.pos_own_hi;
       if (h + r + t == -3) MKE_TRACE(15);  // (forces the id loads to have landed)
       MKE_TRACE(1);
       // the three rows of the positive travel to shared memory while the sampler probes
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         } else {
           for (int c = sub; c < K; c += 8) pick[c] = valid ? __ldg(p.neg_ent + (size_t)i * K + c) : 0;
           side = valid ? __ldg(p.neg_side + i) : 0u;
+          if (p.neg_valid != nullptr && valid) mine = __ldg(p.neg_valid + i);
         }
         __syncwarp();
         if (p.neg_out != nullptr && active) {
@@ -152,13 +155,13 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         }
         float lpos, sg;
         softplus_sigmoid(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
-        const float wgt = (p.w != nullptr && active ? __ldg(p.w + i) : 1.f) * p.pos_scale;
-        if (active) loss_local += wgt * lpos;
+        const float wgt = pos_on ? (p.w != nullptr ? __ldg(p.w + i) : 1.f) * p.pos_scale : 0.f;
+        if (pos_on) loss_local += wgt * lpos;
         const float cp = 2.f * sg * wgt;
 #pragma unroll
         for (int k = 0; k < FPL; ++k) acc[k] *= cp;  // d loss / d pd; the K-loop adds the negatives
         // the endpoint that no same-side negative shares gets its positive-term gradient now
-        if (active && !(p.dbg & 8)) out.add(ent_grad_row(p, side0 ? h : t, stride), acc, sgn);
+        if (pos_on && !(p.dbg & 8)) out.add(ent_grad_row(p, side0 ? h : t, stride), acc, sgn);
       }
       MKE_TRACE(4);
       // ---- negatives: rows j+1, j+2 are in flight while row j is scored ------------------------
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         float lneg, sg;
         softplus_sigmoid(-sn, lneg, sg);  // log(1 + exp(neg_score)), neg_score = -sn
         const bool odd = (((side >> j) & 1u) != 0u) != side0;
-        const bool on = active && !odd;
+        const bool on = active && !odd && ((mine >> j) & 1u) != 0u;
         const float cn = on ? -2.f * sg : 0.f;
         if (on) loss_local += lneg;
 #pragma unroll
@@ -205,11 +208,12 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
       cp_async_wait<0>();
       MKE_TRACE(13);
       // ---- r gets every same-side term, the shared endpoint likewise -----------------------
-      if (active) {
+      if (active && (pos_on || (mine & low_ones(K)) != 0u)) {
         if (!(p.dbg & 1)) out.add(rel_grad + (size_t)r * stride, acc, 1.f);
         if (!(p.dbg & 8)) out.add(ent_grad_row(p, side0 ? t : h, stride), acc, -sgn);
         if (!(p.dbg & 2)) {
-        for (int c = sub; c < K; c += 8) ent_mark(p, pick[c]);
+        for (int c = sub; c < K; c += 8)
+          if ((mine >> c) & 1u) ent_mark(p, pick[c]);
         if (sub == 0) {
           ent_mark(p, h);
           ent_mark(p, t);
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
       const bool mixed = active && side != 0u && side != low_ones(K);
       if (__any_sync(kFull, mixed)) {
         for (int j = 1; j < K; ++j) {
-          const bool odd = active && ((((side >> j) & 1u) != 0u) != side0);
+          const bool odd = active && ((mine >> j) & 1u) != 0u && ((((side >> j) & 1u) != 0u) != side0);
           if (__any_sync(kFull, odd))
             loss_local += odd_negative<FPL>(
                 ent_var_row(p, h, stride), p.rel_var + (size_t)r * stride, ent_var_row(p, t, stride),

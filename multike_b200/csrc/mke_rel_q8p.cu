@@ -20,7 +20,7 @@
 
 namespace mke {
 
-constexpr int kIdStride = 36;  // h r t + MKE_MAX_NEG ids + side word; 2*36 = 8 (mod 32): quarters on distinct banks
+constexpr int kIdStride = 37;  // h r t + MKE_MAX_NEG ids + side word + ownership word; quarters 74 = 10 (mod 32) banks apart
 constexpr int kQ8pThreads = 96;
 constexpr int kQ8pWarps = kQ8pThreads / 32;
 
@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
                                 : (c < R ? (const void*)(nrow + (c - 3)) : (const void*)(p.neg_side + i));
         cp_async4(dst + 4u * c, src);
       }
+      if (p.neg_valid != nullptr && sub == 7) cp_async4(dst + 4u * (R + 1), p.neg_valid + i);
     } else {  // idle quarter of the last pass: row 0 of each table, nothing is written back
-      for (int c = sub; c <= R; c += 8) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + 4u * c), "r"(0) : "memory");
+      for (int c = sub; c <= R + 1; c += 8) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + 4u * c), "r"(0) : "memory");
     }
   };
 
@@ -169,6 +170,9 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
     volatile int32_t* const ids = ids0 + (n & 1) * kIdStride;
     const int32_t h = ids[0], r = ids[1], t = ids[2];
     const uint32_t side = (uint32_t)ids[R];
+    // negatives of this positive that are this launch's, and whether its positive term is
+    const uint32_t mine = p.neg_valid != nullptr ? (uint32_t)ids[R + 1] : 0xffffffffu;
+    const bool pos_on = active && i >= p.pos_own_lo && i < p.pos_own_hi;
     if (n + 1 < passes) ids_issue((n + 1) & 1, i + Q);
     // ---- positive term ---------------------------------------------------------------------
     const bool side0 = (side & 1u) != 0u;  // side of negative 0: true = head replaced
@@ -212,8 +216,8 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       }
       float lpos, sg;
       softplus_sigmoid_mufu(sp, lpos, sg);  // log(1 + exp(-pos_score)), pos_score = -sp (losses.py:7,9)
-      const float wgt = (p.w != nullptr && active ? __ldg(p.w + i) : 1.f) * p.pos_scale;
-      if (active) loss_local += wgt * lpos;
+      const float wgt = pos_on ? (p.w != nullptr ? __ldg(p.w + i) : 1.f) * p.pos_scale : 0.f;
+      if (pos_on) loss_local += wgt * lpos;
       const float cps = 2.f * sg * wgt * sgn;
       float first[FPL];  // sgn * d loss / d pos_distance
 #pragma unroll
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
         accs_t = first[FPL - 1];
       }
       // the endpoint that no same-side negative shares gets its positive-term gradient now
-      if (active) red_row<FPL>(egrad(side0 ? h : t), sub, first, 1.f);
+      if (pos_on) red_row<FPL>(egrad(side0 ? h : t), sub, first, 1.f);
     }
     // ---- negatives ---------------------------------------------------------------------------
 #pragma unroll 1
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       float lneg, sg;
       softplus_sigmoid_mufu(-sn, lneg, sg);  // log(1 + exp(neg_score)), neg_score = -sn
       const bool odd = (((side >> j) & 1u) != 0u) != side0;
-      const bool on = active && !odd;
+      const bool on = active && !odd && ((mine >> j) & 1u) != 0u;
       const float cs = on ? -2.f * sg * sgn : 0.f;  // sgn * d loss / d |nd|^2 * 2
       if (on) loss_local += lneg;
       const float2 sie2 = make_float2(sie, sie), cs2 = make_float2(cs, cs);
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       if (on) red_row<FPL>(egrad(e), sub, y, 1.f);
     }
     // ---- r gets every same-side term, the shared endpoint likewise ---------------------------
-    if (active) {
+    if (active && (pos_on || (mine & low_ones(K)) != 0u)) {
       float a[FPL];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
       if constexpr (ODD) a[FPL - 1] = accs_t;
       red_row<FPL>(rel_grad + (size_t)r * stride, sub, a, sgn);
       red_row<FPL>(egrad(side0 ? t : h), sub, a, -1.f);
-      for (int c = sub; c < K; c += 8) emark(ids[3 + c]);
+      for (int c = sub; c < K; c += 8)
+        if ((mine >> c) & 1u) emark(ids[3 + c]);
       if (sub == 0) {
         emark(h);
         emark(t);
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kQ8pThreads) __maxnreg__(q8p_max_regs(MINB)) r
     const bool mixed = active && side != 0u && side != low_ones(K);
     if (__any_sync(kFull, mixed)) {
       for (int j = 1; j < K; ++j) {
-        const bool odd = active && ((((side >> j) & 1u) != 0u) != side0);
+        const bool odd = active && ((mine >> j) & 1u) != 0u && ((((side >> j) & 1u) != 0u) != side0);
         if (__any_sync(kFull, odd))
           loss_local += odd_negative<FPL>(evar(h), p.rel_var + (size_t)r * stride, evar(t), evar(ids[3 + j]), egrad(h),
                                           rel_grad + (size_t)r * stride, egrad(t), egrad(ids[3 + j]), p.ent_norm,

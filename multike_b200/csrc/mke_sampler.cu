@@ -225,3 +225,50 @@ extern "C" int mke_sample_attribute_heads(const int32_t* pos1, int32_t len1, con
   MKE_CHECK_LAUNCH("attr_sample_kernel");
   return 0;
 }
+
+// ---- "negatives where they live" (sharded.py) ---------------------------------------------------
+// One thread per positive: negatives whose row lives on another shard are replaced by `dummy_id`
+// (a row of this shard: its gather stays local and is served by L1) and their bit in
+// neg_valid[i] is cleared, so the phase-1 kernels skip their contribution.
+namespace mke {
+__global__ void neg_keep_owned_kernel(int32_t* __restrict__ neg_ent, int n, int K, ShardMap smap, int my_shard,
+                                      int32_t dummy_id, uint32_t* __restrict__ neg_valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t mine = 0u;
+  int32_t* row = neg_ent + (size_t)i * K;
+  for (int j = 0; j < K; ++j) {
+    int s;
+    int32_t l;
+    smap.locate(row[j], s, l);
+    if (s == my_shard)
+      mine |= 1u << j;
+    else
+      row[j] = dummy_id;
+  }
+  neg_valid[i] = mine;
+}
+}  // namespace mke
+
+extern "C" int mke_neg_keep_owned(int32_t* neg_ent, int32_t n, int32_t K, int32_t n_shards, int32_t shard_split,
+                                  int32_t my_shard, int32_t dummy_id, uint32_t* neg_valid, mke_stream_t stream) {
+  MKE_CHECK_ARG(n >= 0 && K >= 1 && K <= MKE_MAX_NEG, "bad n / K");
+  MKE_CHECK_ARG(n_shards == 2 || n_shards == 4 || n_shards == 8, "n_shards=%d (2, 4 or 8)", n_shards);
+  MKE_CHECK_ARG(my_shard >= 0 && my_shard < n_shards && shard_split >= 0, "bad shard / split");
+  if (n == 0) return 0;
+  MKE_CHECK_ARG(neg_ent && neg_valid, "null pointer");
+  mke_table_t t{};
+  t.n_shards = n_shards;
+  t.shard_split = shard_split;
+  const mke::ShardMap smap = mke::shard_map(&t);
+  {
+    int s;
+    int32_t l;
+    smap.locate(dummy_id, s, l);
+    MKE_CHECK_ARG(s == my_shard, "dummy row %d does not live on shard %d", dummy_id, my_shard);
+  }
+  mke::neg_keep_owned_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(neg_ent, n, K, smap, my_shard,
+                                                                               dummy_id, neg_valid);
+  MKE_CHECK_LAUNCH("neg_keep_owned_kernel");
+  return 0;
+}

@@ -79,6 +79,20 @@ def rank_parts(n1, n2, global_batch, step, rank, world, by_kg=False):
     return (a1 + s1, t1 - s1), (a2 + s2, t2 - s2), lo
 
 
+def group_parts(n1, n2, global_batch, step, rank, world):
+    """"Negatives where they live" (KG-block placement, world >= 4): every rank of a KG's half of the
+    ranks walks the WHOLE slice of that KG.  Returns (kg (1 or 2), (start, length) of the slice in the
+    KG's triple list, (own_lo, own_hi) = the positions inside the slice whose positive terms this
+    rank computes, index_base = position of the slice's first positive in the global batch)."""
+    b1, b2 = split_batch(n1, n2, global_batch)
+    a1, e1 = clipped_slice(n1, b1, step)
+    a2, e2 = clipped_slice(n2, b2, step)
+    half = world // 2
+    if rank < half:
+        return 1, (a1, e1 - a1), rank_range(e1 - a1, rank, half), 0
+    return 2, (a2, e2 - a2), rank_range(e2 - a2, rank - half, half), e1 - a1
+
+
 # ---------------------------------------------------------------------------------------------
 # peer memory
 # ---------------------------------------------------------------------------------------------
@@ -251,8 +265,18 @@ class ShardedRelationView:
         # half of the ranks, which exceeds batch_size for the larger KG)
         b1, b2 = split_batch(self.n1, self.n2, self.global_batch)
         cap = (max(b1, b2) // max(self.world // 2, 1) + 2) if self.by_kg else self.batch_size + 2
+        # negatives where they live (include/multike_b200.h, mke_neg_keep_owned): with more than one
+        # rank per KG every rank walks its KG's whole slice and scores the negatives it owns
+        self.owner_negs = self.by_kg and self.world >= 4 and self.K > 0 and \
+            os.environ.get("MKE_OWNER_NEGS", "1") == "1"
+        if self.owner_negs:
+            cap = max(b1, b2) + 2
+            half = self.world // 2
+            self._dummy_row = self.rank if self.rank < half else ent_split + (self.rank - half)
         self._neg_ent = torch.empty(cap * max(self.K, 1), dtype=torch.int32, device=self.device)
         self._neg_side = torch.empty(cap, dtype=torch.int32, device=self.device)
+        self._neg_valid = torch.empty(cap, dtype=torch.int32, device=self.device)
+        self.ent_split = int(ent_split)
         self.loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._fence = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.global_step = 0
@@ -265,6 +289,8 @@ class ShardedRelationView:
     def step(self, step_in_epoch):
         """one global step; returns the number of positives this rank trained"""
         import torch.distributed as dist
+        if self.owner_negs:
+            return self._step_owner_negs(step_in_epoch)
         (a1, l1), (a2, l2), base = rank_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank, self.world,
                                                by_kg=self.by_kg)
         stream = _cabi.current_stream()
@@ -295,6 +321,46 @@ class ShardedRelationView:
         dist.all_reduce(self._fence, group=self.group)
         self.global_step += 1
         return l1 + l2
+
+    def _exchange_and_apply(self):
+        import torch.distributed as dist
+        # dense gradient bucket of the replicated relation table; after it, every rank's phase 1
+        # (and with it every peer reduction into this rank's shard) has completed
+        dist.all_reduce(self.rel.grad, group=self.group)
+        T.apply_adagrad_pair(self.ent, self.ent.adagrad_slot(self.SLOT), self.lr,
+                             self.rel, self.rel.adagrad_slot(self.SLOT), self.lr)
+        # no rank may start the next phase 1 before every rank has finished this phase 2
+        dist.all_reduce(self._fence, group=self.group)
+        self.global_step += 1
+
+    def _step_owner_negs(self, step_in_epoch):
+        """one global step under "negatives where they live": the whole slice of this rank's KG, the
+        negatives this rank owns, the positive terms of its share of the slice"""
+        kg_no, (a, ln), (lo, hi), base = group_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank,
+                                                     self.world)
+        stream = _cabi.current_stream()
+        first = kg_no == 1
+        p1 = self.triples1.data_ptr() + 12 * a if first else None
+        p2 = None if first else self.triples2.data_ptr() + 12 * a
+        l1, l2 = (ln, 0) if first else (0, ln)
+        if ln > 0:
+            _cabi.check(self._lib.mke_sample_structured_at(
+                p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), self.global_step, base,
+                self._neg_ent.data_ptr(), self._neg_side.data_ptr(), stream))
+            _cabi.check(self._lib.mke_neg_keep_owned(self._neg_ent.data_ptr(), ln, self.K, self.world, self.ent_split,
+                                                     self.rank, self._dummy_row, self._neg_valid.data_ptr(), stream))
+            ev = None
+            if self.phase1_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            _cabi.check(self._lib.mke_rel_step_structured3(
+                self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent.data_ptr(), self._neg_side.data_ptr(),
+                self._neg_valid.data_ptr(), lo, hi, None, 1.0, self.loss_acc.data_ptr(), self.variant, stream))
+            if ev is not None:
+                ev[1].record()
+                self.phase1_events.append(ev)
+        self._exchange_and_apply()
+        return hi - lo
 
     def train_epoch(self):
         import torch.distributed as dist

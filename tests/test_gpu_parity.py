@@ -539,6 +539,50 @@ def test_full_size_row_stream_schedule_equals_one_wave_kernel(G, full):
     torch.testing.assert_close(a[5], b[5], rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("world", [4, 8])
+def test_negatives_where_they_live_decomposition(G, full, world, variant):
+    """mke_neg_keep_owned + mke_rel_step_structured3 (the multi-GPU scheme of sharded.py, run here as
+    `world` launches into ONE table): every virtual rank walks all positives of its KG but scores only
+    the negatives whose entity it would own, and the positive terms of its slice of the batch; the sum
+    over the ranks must equal one ordinary step -- loss, gradient rows and touched flags."""
+    U, T = G
+    from multike_b200.sharded import rank_range, shard_owner
+    kgs, ent0, rel0, kg1, kg2 = full
+    K, B1, B2 = 10, 10159, 9841
+    split, half = kgs["ent_split"], world // 2
+    p1 = torch.as_tensor(kgs["triples1"][3 * B1:4 * B1]).cuda()
+    p2 = torch.as_tensor(kgs["triples2"][3 * B2:4 * B2]).cuda()
+    neg_ent, neg_side = T.sample_structured(p1, kg1, p2, kg2, K, 5, 9)
+    ent, rel = U.make_tables(ent0.numpy(), rel0.numpy())
+    acc = T.new_loss_accumulator()
+    T.rel_step_structured(ent, rel, torch.cat([p1, p2]), neg_ent, neg_side, K, acc, variant=variant)
+    want = (U.loss_value(acc), ent.grad_sum().clone(), rel.grad_sum().clone(), ent.touched.clone())
+    ent, rel = U.make_tables(ent0.numpy(), rel0.numpy())
+    acc = T.new_loss_accumulator()
+    kept = 0
+    for rank in range(world):
+        first = rank < half
+        pos = p1 if first else p2
+        ne = (neg_ent[:B1] if first else neg_ent[B1:]).clone()
+        ns = (neg_side[:B1] if first else neg_side[B1:]).contiguous()
+        dummy = rank if first else split + (rank - half)
+        valid = T.neg_keep_owned(ne, K, world, split, rank, dummy)
+        # the mask is exactly "owner == rank", and foreign slots now hold the dummy row
+        owner, _ = shard_owner((neg_ent[:B1] if first else neg_ent[B1:]).cpu().numpy(), world, split)
+        bits = ((valid.cpu().numpy().astype(np.int64)[:, None] >> np.arange(K)) & 1).astype(bool)
+        assert np.array_equal(bits, owner == rank)
+        assert bool((ne.cpu().numpy()[~bits] == dummy).all())
+        kept += int(bits.sum())
+        lo, hi = rank_range(len(pos), rank % half, half)
+        T.rel_step_owned(ent, rel, pos, ne, ns, valid, lo, hi, K, acc, variant=variant)
+    assert kept == (B1 + B2) * K
+    assert U.loss_value(acc) == pytest.approx(want[0], rel=1e-6)
+    torch.testing.assert_close(ent.grad_sum(), want[1], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(rel.grad_sum(), want[2], rtol=1e-4, atol=2e-4)
+    assert torch.equal(ent.touched, want[3])
+
+
 def test_pair_apply_equals_two_single_applies(G, golden):
     """mke_rows_apply_adagrad_pair (one launch for the entity + relation table) == two calls of
     mke_rows_apply_adagrad, bit for bit; different learning rates per table are honoured."""

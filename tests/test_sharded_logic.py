@@ -51,6 +51,20 @@ def test_rank_parts_partition_the_global_batch():
             assert np.array_equal(local[owner == r], np.arange(mine.size))  # local rows are dense, in id order
 
 
+def test_group_parts_own_ranges_are_the_by_kg_partition():
+    """negatives where they live: a rank walks its KG's whole slice, and the positions whose
+    positive terms it computes are exactly the slice rank_parts(by_kg=True) gives it"""
+    from multike_b200.sharded import group_parts, rank_parts
+    for n1, n2, gb, world in [(463294, 448774, 80000, 4), (463294, 448774, 160000, 8), (700, 500, 200, 4), (10, 1000, 64, 8)]:
+        steps = -(-(n1 + n2) // gb)
+        for step in list(range(min(steps, 3))) + [steps - 1]:
+            for rank in range(world):
+                kg, (a, ln), (lo, hi), base = group_parts(n1, n2, gb, step, rank, world)
+                (a1, l1), (a2, l2), b = rank_parts(n1, n2, gb, step, rank, world, by_kg=True)
+                assert kg == (1 if rank < world // 2 else 2) and 0 <= lo <= hi <= ln
+                assert (a + lo, hi - lo) == ((a1, l1) if kg == 1 else (a2, l2)) and base + lo == b
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
