@@ -238,9 +238,13 @@ class ShardedRelationView:
         import torch.distributed as dist
         self._lib = _cabi.load()
         # phase-1 schedule (include/multike_b200.h `variant`); MKE_SHARDED_VARIANT is an experiment knob
-        self.variant = int(os.environ.get("MKE_SHARDED_VARIANT", "0")) if variant is None else int(variant)
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        # measured on 4 x B200: with rows behind NVLink the one-wave kernel (all of a positive's remote
+        # rows requested up front) beats the in-order row stream; without remote rows (2 ranks, one KG
+        # each) the row stream is the faster one
+        default_variant = "3" if (self.world == 2 and by_kg) else "0"
+        self.variant = int(os.environ.get("MKE_SHARDED_VARIANT", default_variant)) if variant is None else int(variant)
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.dim, self.K, self.lr, self.seed = int(dim), int(neg_num), float(lr), int(seed)
         self.batch_size = int(batch_size)              # per rank
@@ -273,10 +277,15 @@ class ShardedRelationView:
             cap = max(b1, b2) + 2
             half = self.world // 2
             self._dummy_row = self.rank if self.rank < half else ent_split + (self.rank - half)
-        self._neg_ent = torch.empty(cap * max(self.K, 1), dtype=torch.int32, device=self.device)
-        self._neg_side = torch.empty(cap, dtype=torch.int32, device=self.device)
-        self._neg_valid = torch.empty(cap, dtype=torch.int32, device=self.device)
+        # two buffer sets: the negatives of step s + 1 are drawn while step s is exchanged and applied
+        self._neg_ent = torch.empty(2, cap * max(self.K, 1), dtype=torch.int32, device=self.device)
+        self._neg_side = torch.empty(2, cap, dtype=torch.int32, device=self.device)
+        self._neg_valid = torch.empty(2, cap, dtype=torch.int32, device=self.device)
         self.ent_split = int(ent_split)
+        self.draw_ahead = os.environ.get("MKE_DRAW_AHEAD", "1") == "1"
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ahead = None        # ((step_in_epoch, global_step, list version), buffer set, ready event)
+        self._list_version = 0    # bump when the triple lists are permuted (a prefetch would be stale)
         self.loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._fence = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.global_step = 0
@@ -286,31 +295,73 @@ class ShardedRelationView:
     def triple_steps(self):
         return int(math.ceil((self.n1 + self.n2) / self.global_batch))
 
-    def step(self, step_in_epoch):
-        """one global step; returns the number of positives this rank trained"""
-        import torch.distributed as dist
+    def _plan(self, step_in_epoch):
+        """launch arguments of one global step for this rank: (p1, l1, p2, l2, index_base, own_lo,
+        own_hi, positives this rank answers for)"""
         if self.owner_negs:
-            return self._step_owner_negs(step_in_epoch)
+            kg_no, (a, ln), (lo, hi), base = group_parts(self.n1, self.n2, self.global_batch, step_in_epoch,
+                                                         self.rank, self.world)
+            if kg_no == 1:
+                return self.triples1.data_ptr() + 12 * a, ln, None, 0, base, lo, hi, hi - lo
+            return None, 0, self.triples2.data_ptr() + 12 * a, ln, base, lo, hi, hi - lo
         (a1, l1), (a2, l2), base = rank_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank, self.world,
                                                by_kg=self.by_kg)
+        return (self.triples1.data_ptr() + 12 * a1, l1, self.triples2.data_ptr() + 12 * a2, l2, base, 0, 0x7fffffff,
+                l1 + l2)
+
+    def _draw(self, plan, global_step, buf):
+        """negatives of a step into buffer set `buf` on the current stream (sampler, then the
+        ownership filter under "negatives where they live")"""
+        p1, l1, p2, l2, base = plan[:5]
+        if self.K == 0 or l1 + l2 == 0:
+            return
         stream = _cabi.current_stream()
-        p1 = self.triples1.data_ptr() + 12 * a1
-        p2 = self.triples2.data_ptr() + 12 * a2
+        ne, ns, nv = self._neg_ent[buf], self._neg_side[buf], self._neg_valid[buf]
+        _cabi.check(self._lib.mke_sample_structured_at(
+            p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), global_step, base,
+            ne.data_ptr(), ns.data_ptr(), stream))
+        if self.owner_negs:
+            _cabi.check(self._lib.mke_neg_keep_owned(ne.data_ptr(), l1 + l2, self.K, self.world, self.ent_split,
+                                                     self.rank, self._dummy_row, nv.data_ptr(), stream))
+
+    def step(self, step_in_epoch):
+        """one global step; returns the number of positives this rank answers for.  The negatives of
+        the NEXT step are drawn on a side stream while this step's collectives and phase 2 run."""
+        import torch.distributed as dist
+        main = torch.cuda.current_stream()
+        plan = self._plan(step_in_epoch)
+        p1, l1, p2, l2, base, lo, hi, mine = plan
+        key = (step_in_epoch, self.global_step, self._list_version)
+        if self._ahead is not None and self._ahead[0] == key:
+            buf = self._ahead[1]
+            main.wait_event(self._ahead[2])
+        else:
+            buf = 0 if self._ahead is None else 1 - self._ahead[1]
+            self._draw(plan, self.global_step, buf)
+        self._ahead = None
         if l1 + l2 > 0:
-            if self.K > 0:
-                _cabi.check(self._lib.mke_sample_structured_at(
-                    p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), self.global_step, base,
-                    self._neg_ent.data_ptr(), self._neg_side.data_ptr(), stream))
             ev = None
             if self.phase1_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            _cabi.check(self._lib.mke_rel_step_structured2(
-                self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent.data_ptr(), self._neg_side.data_ptr(),
-                None, 1.0, self.loss_acc.data_ptr(), self.variant, stream))
+            _cabi.check(self._lib.mke_rel_step_structured3(
+                self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent[buf].data_ptr(),
+                self._neg_side[buf].data_ptr(), self._neg_valid[buf].data_ptr() if self.owner_negs else None, lo, hi,
+                None, 1.0, self.loss_acc.data_ptr(), self.variant, main.cuda_stream))
             if ev is not None:
                 ev[1].record()
                 self.phase1_events.append(ev)
+        if self.K > 0 and self.draw_ahead:
+            # the other buffer set was last read by the previous phase 1, which precedes this event
+            nxt = (step_in_epoch + 1) % self.triple_steps
+            done = torch.cuda.Event()
+            done.record(main)
+            self._side.wait_event(done)
+            with torch.cuda.stream(self._side):
+                self._draw(self._plan(nxt), self.global_step + 1, 1 - buf)
+                ready = torch.cuda.Event()
+                ready.record(self._side)
+            self._ahead = ((nxt, self.global_step + 1, self._list_version), 1 - buf, ready)
         # dense gradient bucket of the replicated relation table; after it, every rank's phase 1
         # (and with it every peer reduction into this rank's shard) has completed
         dist.all_reduce(self.rel.grad, group=self.group)
@@ -320,47 +371,7 @@ class ShardedRelationView:
         # every rank has finished this phase 2: a stream-ordered one-element all-reduce (no host sync)
         dist.all_reduce(self._fence, group=self.group)
         self.global_step += 1
-        return l1 + l2
-
-    def _exchange_and_apply(self):
-        import torch.distributed as dist
-        # dense gradient bucket of the replicated relation table; after it, every rank's phase 1
-        # (and with it every peer reduction into this rank's shard) has completed
-        dist.all_reduce(self.rel.grad, group=self.group)
-        T.apply_adagrad_pair(self.ent, self.ent.adagrad_slot(self.SLOT), self.lr,
-                             self.rel, self.rel.adagrad_slot(self.SLOT), self.lr)
-        # no rank may start the next phase 1 before every rank has finished this phase 2
-        dist.all_reduce(self._fence, group=self.group)
-        self.global_step += 1
-
-    def _step_owner_negs(self, step_in_epoch):
-        """one global step under "negatives where they live": the whole slice of this rank's KG, the
-        negatives this rank owns, the positive terms of its share of the slice"""
-        kg_no, (a, ln), (lo, hi), base = group_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank,
-                                                     self.world)
-        stream = _cabi.current_stream()
-        first = kg_no == 1
-        p1 = self.triples1.data_ptr() + 12 * a if first else None
-        p2 = None if first else self.triples2.data_ptr() + 12 * a
-        l1, l2 = (ln, 0) if first else (0, ln)
-        if ln > 0:
-            _cabi.check(self._lib.mke_sample_structured_at(
-                p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), self.global_step, base,
-                self._neg_ent.data_ptr(), self._neg_side.data_ptr(), stream))
-            _cabi.check(self._lib.mke_neg_keep_owned(self._neg_ent.data_ptr(), ln, self.K, self.world, self.ent_split,
-                                                     self.rank, self._dummy_row, self._neg_valid.data_ptr(), stream))
-            ev = None
-            if self.phase1_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            _cabi.check(self._lib.mke_rel_step_structured3(
-                self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent.data_ptr(), self._neg_side.data_ptr(),
-                self._neg_valid.data_ptr(), lo, hi, None, 1.0, self.loss_acc.data_ptr(), self.variant, stream))
-            if ev is not None:
-                ev[1].record()
-                self.phase1_events.append(ev)
-        self._exchange_and_apply()
-        return hi - lo
+        return mine
 
     def train_epoch(self):
         import torch.distributed as dist

@@ -1,17 +1,17 @@
 #!/bin/bash
-# Multi-GPU session (run under `gpurun --gpus 4`): correctness of the row-sharded relation view with
-# both phase-1 schedules, then bench lines at N = 2 and N = 4 for each.
+# Multi-GPU session (run under `gpurun --gpus N`): correctness of the row-sharded relation view under
+# "negatives where they live" with both phase-1 schedules, then bench lines against the old scheme.
 out=gpurun_out/multi_$1
 mkdir -p $out
 N=${2:-4}
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
-for v in 0 3; do
-  MKE_SHARDED_VARIANT=$v run $N 29601 tests/multi_gpu_check.py > $out/check_n${N}_v$v.log 2>&1; grep MULTI_GPU_CHECK $out/check_n${N}_v$v.log || tail -5 $out/check_n${N}_v$v.log
-done
-for n in 2 $N; do
-  for v in 0 3; do
-    MKE_SHARDED_VARIANT=$v run $n 29611 bench.py --gpus $n --steps 200 --warmup 20 > $out/bench_n${n}_v$v.json 2> $out/bench_n${n}_v$v.err
-    python - $out/bench_n${n}_v$v.json n${n}_v$v <<'PY'
+run $N 29601 tests/multi_gpu_check.py > $out/check_n${N}.log 2>&1; grep MULTI_GPU_CHECK $out/check_n${N}.log || tail -5 $out/check_n${N}.log
+MKE_BY_KG=0 run $N 29602 tests/multi_gpu_check.py > $out/check_n${N}_mod.log 2>&1; grep MULTI_GPU_CHECK $out/check_n${N}_mod.log || tail -5 $out/check_n${N}_mod.log
+run 2 29603 tests/multi_gpu_check.py > $out/check_n2.log 2>&1; grep MULTI_GPU_CHECK $out/check_n2.log || tail -5 $out/check_n2.log
+bench() {  # name, n, env...
+  name=$1; n=$2; shift 2
+  env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $n --steps 200 --warmup 20 > $out/$name.json 2> $out/$name.err
+  python - $out/$name.json $name <<'PY'
 import json,sys
 try:
     j=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -19,6 +19,8 @@ try:
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
-  done
-done
-python bench.py --no-cpu-baseline > $out/bench_n1.json 2>$out/bench_n1.err; tail -c 600 $out/bench_n1.json
+}
+bench n${N}_default $N X=1
+bench n${N}_inline $N MKE_DRAW_AHEAD=0
+bench n2_default 2 X=1
+bench n2_inline 2 MKE_DRAW_AHEAD=0
