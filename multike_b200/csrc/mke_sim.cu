@@ -12,7 +12,7 @@
 // The contraction is 75..128 deep and has to order near-ties like the reference's fp32 sgemm, so
 // it runs on the fp32 FMA pipe (no tensor cores: tf32/bf16 would reorder the ranks): one thread
 // block owns a 128-row tile of A, streams 128-row tiles of B through a double-buffered cp.async
-// stage and keeps an 8 x 8 block of sims per thread in registers.  Every sim is the sum of two fmaf
+// stage and keeps a 16 x 4 block of sims per thread in registers.  Every sim is the sum of two fmaf
 // chains in ascending k (even and odd columns, packed FFMA2) -- the same two chains
 // sim_gold_kernel uses -- so equal rows give bit-equal sims and the tie rules below are exact.
 #include "mke_common.cuh"
@@ -20,7 +20,7 @@
 namespace mke {
 
 constexpr int kSimTile = 128;     // rows of A / of B per tile
-constexpr int kSimThreads = 256;  // 16 x 16 threads, 8 x 8 sims each
+constexpr int kSimThreads = 256;  // 8 warps x 32 lanes, 16 x 4 sims each
 constexpr int kSimMaxWs = 128;    // workspace row stride supported by the shared-memory stage
 
 // order-preserving map float -> uint32 (larger float => larger key; -0 < +0)
@@ -117,13 +117,20 @@ __device__ __forceinline__ void sim_load_tile(uint32_t tile, const float* __rest
 template <bool RANK>
 __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParams p) {
   extern __shared__ __align__(16) float s_sim[];
+  __shared__ float s_sg[kSimTile];
+  __shared__ int s_gi[kSimTile];
   const int pitch = p.ws + 4;  // (pitch / 4) odd: the 8 lanes of a 128-bit phase hit 8 bank groups
   float* const As = s_sim;
   float* const Bs0 = s_sim + kSimTile * pitch;
   const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(As);
   const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(Bs0);
   const uint32_t tile_bytes = (uint32_t)(kSimTile * pitch * 4);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // Thread layout: warp w owns the 16 rows [16 w, 16 w + 16) of the A tile, lane l the 4 columns
+  // {l + 32 j} of the B tile.  Every A read is one address per warp (a broadcast: one shared-memory
+  // wavefront instead of four), every B read is conflict free, and a row's 32 sims of a store are
+  // one 128-byte segment.  Per 4 embedding columns a thread issues 20 LDS.128 for 128 FFMA2.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int RI = 16, CJ = 4;
   const int rb = blockIdx.x / p.splits, cs = blockIdx.x - rb * p.splits;
   const int row0 = p.row_base + rb * kSimTile;
   const int row_end = p.row_base + p.rows < p.n1 ? p.row_base + p.rows : p.n1;
@@ -133,19 +140,18 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
   if (cs < ntiles) sim_load_tile(b_addr, p.b, p.n2, cs * kSimTile, p.ws, pitch);
   asm volatile("cp.async.commit_group;" ::: "memory");
 
-  // rank mode: per owned row (ty + 16 i) the gold score / column, the count and the running arg-max
-  float sg[8];
-  int gi[8], cnt[8], bi[8];
-  float bs[8];
+  // rank mode: gold score / column of the tile's rows (shared), per thread the count and the running
+  // arg-max of its 16 rows over its columns
+  if (RANK && threadIdx.x < kSimTile) {
+    const int r = row0 + threadIdx.x;
+    const bool ok = r < row_end;
+    s_sg[threadIdx.x] = ok ? __ldg(p.gold_score + r) : __int_as_float(0x7f800000);
+    s_gi[threadIdx.x] = ok ? (p.gold ? __ldg(p.gold + r) : r) : -1;
+  }
+  int cnt[RI], bi[RI];
+  float bs[RI];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = row0 + ty + 16 * i;
-    sg[i] = __int_as_float(0x7f800000);
-    gi[i] = -1;
-    if (RANK && r < row_end) {
-      sg[i] = __ldg(p.gold_score + r);
-      gi[i] = p.gold ? __ldg(p.gold + r) : r;
-    }
+  for (int i = 0; i < RI; ++i) {
     cnt[i] = 0;
     bi[i] = 0x7fffffff;
     bs[i] = __int_as_float(0xff800000);
@@ -158,52 +164,53 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
-    const float* At = As + ty * pitch;
-    const float* Bt = Bs0 + (size_t)buf * kSimTile * pitch + tx * pitch;
+    const float* At = As + (warp * RI) * pitch;
+    const float* Bt = Bs0 + (size_t)buf * kSimTile * pitch + lane * pitch;
     // Packed fp32 (fma.rn.f32x2, SASS FFMA2): every sim is accumulated as two chains -- the even
     // and the odd columns of the embedding -- that ride in one 64-bit register pair and are added
-    // at the end; one issue slot feeds two FMAs, which is what lifts the scalar-FFMA issue limit.
-    float2 acc2[8][8];
+    // at the end; one issue slot feeds two FMAs.
+    float2 acc2[RI][CJ];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < CJ; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int k4 = 0; k4 < (p.ws >> 2); ++k4) {
-      float4 a[8];
+      float2 b01[CJ], b23[CJ];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(At + 16 * i * pitch + 4 * k4);
+      for (int j = 0; j < CJ; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(Bt + 32 * j * pitch + 4 * k4);
+        b01[j] = make_float2(b.x, b.y);
+        b23[j] = make_float2(b.z, b.w);
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = *reinterpret_cast<const float4*>(Bt + 16 * j * pitch + 4 * k4);
-        const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
+      for (int i = 0; i < RI; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(At + i * pitch + 4 * k4);
+        const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int j = 0; j < CJ; ++j) {
           float2 v = acc2[i][j];
-          v = __ffma2_rn(make_float2(a[i].x, a[i].y), b01, v);
-          v = __ffma2_rn(make_float2(a[i].z, a[i].w), b23, v);
+          v = __ffma2_rn(a01, b01[j], v);
+          v = __ffma2_rn(a23, b23[j], v);
           acc2[i][j] = v;
         }
       }
     }
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
     // ---- epilogue of this tile ----------------------------------------------------------------
-    const int col0 = jt * kSimTile + tx;
+    const int col0 = jt * kSimTile + lane;
     if constexpr (RANK) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = col0 + 16 * j;
-        const bool cv = col < p.n2;
+      for (int i = 0; i < RI; ++i) {
+        const float sg = s_sg[warp * RI + i];
+        const int gi = s_gi[warp * RI + i];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float s = acc[i][j];
+        for (int j = 0; j < CJ; ++j) {
+          const int col = col0 + 32 * j;
+          const bool cv = col < p.n2;
+          const float s = acc2[i][j].x + acc2[i][j].y;
           // stable descending order (base/alignment.py:148 argsort of -sim): a column ranks before
           // the gold one if its sim is larger, or equal with a smaller column index
-          const bool before = cv && col != gi[i] && (s > sg[i] || (s == sg[i] && col < gi[i]));
+          const bool before = cv && col != gi && (s > sg || (s == sg && col < gi));
           cnt[i] += before ? 1 : 0;
           if (cv && s > bs[i]) {  // this thread sees its columns in ascending order
             bs[i] = s;
@@ -213,14 +220,14 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + ty + 16 * i;
+      for (int i = 0; i < RI; ++i) {
+        const int r = row0 + warp * RI + i;
         if (r < row_end) {
           float* o = p.out + (size_t)(r - p.row_base) * p.out_pitch;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = col0 + 16 * j;
-            if (col < p.n2) o[col] = acc[i][j];
+          for (int j = 0; j < CJ; ++j) {
+            const int col = col0 + 32 * j;
+            if (col < p.n2) o[col] = acc2[i][j].x + acc2[i][j].y;
           }
         }
       }
@@ -230,20 +237,20 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if constexpr (RANK) {
-    // the 16 threads of a row (one half warp) combine, then one atomic per row and block
+    // the 32 lanes of a warp combine their columns, then one atomic per row and block
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < RI; ++i) {
       int c = cnt[i];
       unsigned long long key =
           bi[i] == 0x7fffffff ? 0ull : (((unsigned long long)ord_key(bs[i]) << 32) | (0xFFFFFFFFu - (uint32_t)bi[i]));
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
+      for (int o = 16; o > 0; o >>= 1) {
         c += __shfl_xor_sync(0xffffffffu, c, o);
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other > key ? other : key;
       }
-      const int r = row0 + ty + 16 * i;
-      if (tx == 0 && r < row_end) {
+      const int r = row0 + warp * RI + i;
+      if (lane == 0 && r < row_end) {
         if (c != 0) atomicAdd(p.rank + r, c);
         atomicMax(p.best + r, key);
       }

@@ -286,6 +286,8 @@ class ShardedRelationView:
         # than the 15-20 us of sampling they hide (4 x B200: 430 vs 539 M positives/s)
         self.draw_ahead = os.environ.get("MKE_DRAW_AHEAD", "0") == "1"
         self._side = torch.cuda.Stream(device=self.device)
+        self._events = [(torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
+        self._plans = {}
         self._ahead = None        # ((step_in_epoch, global_step, list version), buffer set, ready event)
         self._list_version = 0    # bump when the triple lists are permuted (a prefetch would be stale)
         self.loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -299,7 +301,14 @@ class ShardedRelationView:
 
     def _plan(self, step_in_epoch):
         """launch arguments of one global step for this rank: (p1, l1, p2, l2, index_base, own_lo,
-        own_hi, positives this rank answers for)"""
+        own_hi, positives this rank answers for); a pure function of the step (lists are permuted in
+        place), so it is computed once per step of an epoch"""
+        plan = self._plans.get(step_in_epoch)
+        if plan is None:
+            plan = self._plans[step_in_epoch] = self._make_plan(step_in_epoch)
+        return plan
+
+    def _make_plan(self, step_in_epoch):
         if self.owner_negs:
             kg_no, (a, ln), (lo, hi), base = group_parts(self.n1, self.n2, self.global_batch, step_in_epoch,
                                                          self.rank, self.world)
@@ -311,13 +320,12 @@ class ShardedRelationView:
         return (self.triples1.data_ptr() + 12 * a1, l1, self.triples2.data_ptr() + 12 * a2, l2, base, 0, 0x7fffffff,
                 l1 + l2)
 
-    def _draw(self, plan, global_step, buf):
-        """negatives of a step into buffer set `buf` on the current stream (sampler, then the
-        ownership filter under "negatives where they live")"""
+    def _draw(self, plan, global_step, buf, stream):
+        """negatives of a step into buffer set `buf` on `stream` (sampler, then the ownership
+        filter under "negatives where they live")"""
         p1, l1, p2, l2, base = plan[:5]
         if self.K == 0 or l1 + l2 == 0:
             return
-        stream = _cabi.current_stream()
         ne, ns, nv = self._neg_ent[buf], self._neg_side[buf], self._neg_valid[buf]
         _cabi.check(self._lib.mke_sample_structured_at(
             p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), global_step, base,
@@ -339,7 +347,7 @@ class ShardedRelationView:
             main.wait_event(self._ahead[2])
         else:
             buf = 0 if self._ahead is None else 1 - self._ahead[1]
-            self._draw(plan, self.global_step, buf)
+            self._draw(plan, self.global_step, buf, main.cuda_stream)
         self._ahead = None
         if l1 + l2 > 0:
             ev = None
@@ -356,13 +364,11 @@ class ShardedRelationView:
         if self.K > 0 and self.draw_ahead:
             # the other buffer set was last read by the previous phase 1, which precedes this event
             nxt = (step_in_epoch + 1) % self.triple_steps
-            done = torch.cuda.Event()
+            done, ready = self._events[buf]
             done.record(main)
             self._side.wait_event(done)
-            with torch.cuda.stream(self._side):
-                self._draw(self._plan(nxt), self.global_step + 1, 1 - buf)
-                ready = torch.cuda.Event()
-                ready.record(self._side)
+            self._draw(self._plan(nxt), self.global_step + 1, 1 - buf, self._side.cuda_stream)
+            ready.record(self._side)
             self._ahead = ((nxt, self.global_step + 1, self._list_version), 1 - buf, ready)
         # dense gradient bucket of the replicated relation table; after it, every rank's phase 1
         # (and with it every peer reduction into this rank's shard) has completed

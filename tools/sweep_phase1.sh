@@ -15,16 +15,7 @@ PY
 }
 B="python bench.py --no-cpu-baseline --steps 460 --warmup 46"
 b v0 $B --variant 0
-b v3_b6 env MKE_Q8P_BLOCKS=6 $B --variant 3
-b v3_b5 env MKE_Q8P_BLOCKS=5 $B --variant 3
-b v3_b4 env MKE_Q8P_BLOCKS=4 $B --variant 3
-b v3_roomy_b5 env MKE_Q8_CFG=11 MKE_Q8P_BLOCKS=5 $B --variant 0
-b v3_roomy_b4 env MKE_Q8_CFG=11 MKE_Q8P_BLOCKS=4 $B --variant 0
-b v3_d4_b6 env MKE_Q8_CFG=12 MKE_Q8P_BLOCKS=6 $B --variant 0
-b v0_again $B --variant 0
-b v3_again $B --variant 3
-b big_v0 $B --variant 0 --workload synth1m_rel_d128_b20000_k25 --steps 200 --warmup 20
-b big_v3 $B --variant 3 --workload synth1m_rel_d128_b20000_k25 --steps 200 --warmup 20
+b v3 $B --variant 3
 python tools/bench_sim.py > $out/sim.json 2> $out/sim.err; cat $out/sim.json; tail -3 $out/sim.err
-ncu --set full --clock-control none --import-source on -k regex:rel_fused_q8p -s 20 -c 2 -o $out/ncu_q8p python bench.py --no-cpu-baseline --steps 30 --warmup 5 --variant 3 > $out/ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"sim_tile" -c 2 -o $out/ncu_sim python tools/bench_sim.py --profile > $out/ncu_sim.log 2>&1
 ls $out
