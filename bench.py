@@ -317,12 +317,16 @@ def main():
     # how much of a CUDA-event pair is not the kernel: the same pair around a one-row fill kernel
     probe = torch.zeros(8, device="cuda")
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+    ballast = torch.empty(1 << 28, dtype=torch.float32, device="cuda")
+    for _ in range(8):  # ~2 ms of queued device work, so that the pairs below are enqueued AHEAD of the GPU
+        ballast.zero_()
     for a, b in pairs:
         a.record()
         _cabi.check(lib.mke_fill_rows(probe.data_ptr(), 1, 8, 8, 0.0, _cabi.current_stream()))
         b.record()
     torch.cuda.synchronize()
     event_floor_ms = sorted(a.elapsed_time(b) for a, b in pairs)[len(pairs) // 2]
+    del ballast
 
     # ---- end-to-end leg: every step copies its positives in from pinned HOST memory and its
     # loss back out (mke_rel_view_t.host_triples / host_step_loss); one sync at the end --------

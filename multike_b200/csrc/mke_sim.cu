@@ -12,7 +12,7 @@
 // The contraction is 75..128 deep and has to order near-ties like the reference's fp32 sgemm, so
 // it runs on the fp32 FMA pipe (no tensor cores: tf32/bf16 would reorder the ranks): one thread
 // block owns a 128-row tile of A, streams 128-row tiles of B through a double-buffered cp.async
-// stage and keeps a 16 x 4 block of sims per thread in registers.  Every sim is the sum of two fmaf
+// stage and keeps an 8 x 4 block of sims per thread in registers.  Every sim is the sum of two fmaf
 // chains in ascending k (even and odd columns, packed FFMA2) -- the same two chains
 // sim_gold_kernel uses -- so equal rows give bit-equal sims and the tie rules below are exact.
 #include "mke_common.cuh"
@@ -20,7 +20,7 @@
 namespace mke {
 
 constexpr int kSimTile = 128;     // rows of A / of B per tile
-constexpr int kSimThreads = 256;  // 8 warps x 32 lanes, 16 x 4 sims each
+constexpr int kSimThreads = 512;  // 16 warps x 32 lanes, 8 x 4 sims each: 4 warps per scheduler hide the LDS latency
 constexpr int kSimMaxWs = 128;    // workspace row stride supported by the shared-memory stage
 
 // order-preserving map float -> uint32 (larger float => larger key; -0 < +0)
@@ -125,12 +125,12 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
   const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(As);
   const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(Bs0);
   const uint32_t tile_bytes = (uint32_t)(kSimTile * pitch * 4);
-  // Thread layout: warp w owns the 16 rows [16 w, 16 w + 16) of the A tile, lane l the 4 columns
+  // Thread layout: warp w owns the 8 rows [8 w, 8 w + 8) of the A tile, lane l the 4 columns
   // {l + 32 j} of the B tile.  Every A read is one address per warp (a broadcast: one shared-memory
   // wavefront instead of four), every B read is conflict free, and a row's 32 sims of a store are
-  // one 128-byte segment.  Per 4 embedding columns a thread issues 20 LDS.128 for 128 FFMA2.
+  // one 128-byte segment.  Per 4 embedding columns a thread issues 12 LDS.128 for 64 FFMA2.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int RI = 16, CJ = 4;
+  constexpr int RI = kSimTile / (kSimThreads / 32), CJ = 4;
   const int rb = blockIdx.x / p.splits, cs = blockIdx.x - rb * p.splits;
   const int row0 = p.row_base + rb * kSimTile;
   const int row_end = p.row_base + p.rows < p.n1 ? p.row_base + p.rows : p.n1;
