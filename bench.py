@@ -252,6 +252,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="draw negatives inside the fused kernel")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--p1-every", type=int, default=1,
+                    help="put the CUDA-event pair around one phase-1 launch in N of the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -298,7 +300,8 @@ def main():
     barrier()
     if rank == 0:
         clocks.start()
-    _cabi.check(lib.mke_timing_enable(args.steps))  # CUDA events around every phase-1 launch
+    _cabi.check(lib.mke_timing_enable(args.steps))  # CUDA events around the phase-1 launches
+    _cabi.check(lib.mke_timing_stride(max(1, args.p1_every)))
     launches0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -380,7 +383,7 @@ def main():
                          "traffic": ncu_traffic(args.workload, P1_KERNEL[args.variant]),
                          "traffic_note": "dram bytes per launch, ncu --set full (cold L2), profiles/r1_traffic.json",
                          "algorithmic_bytes": alg_bytes, "kernel": P1_KERNEL[args.variant] + " (phase 1)",
-                         "peak_source": peak_kind, "launch_ms": p1_ms,
+                         "peak_source": peak_kind, "launch_ms": p1_ms, "timed_launches": int(cnt.value),
                          "bytes_per_positive": bytes_per_positive(dim, K),
                          "event_pair_floor_ms": event_floor_ms,
                          "event_pair_floor_note": "median of the same CUDA-event pair around a one-row fill kernel: "

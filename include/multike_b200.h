@@ -313,6 +313,8 @@ int mke_rel_train_steps(const mke_rel_view_t* view, int32_t first_step, int32_t 
  */
 int mke_timing_enable(int32_t max_launches);
 int mke_timing_read(double* total_ms, int32_t* launches);
+/* time one phase-1 launch in `every` (default 1): the pair of timed events is itself a few microseconds of the step */
+int mke_timing_stride(int32_t every);
 
 /* ------------------------------------------------------------------------------------------
  * Sampler pieces (base/batch.py:86-116, attr_batch.py:13-25) usable on their own.

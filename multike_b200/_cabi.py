@@ -98,6 +98,7 @@ SIGNATURES = {
     "mke_dense_logistic_fwd_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mke_dense_sqdist_fwd_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mke_timing_enable": (_i32, [_i32]),
+    "mke_timing_stride": (_i32, [_i32]),
     "mke_timing_read": (_i32, [_c.POINTER(_c.c_double), _c.POINTER(_i32)]),
     "mke_rows_apply_adagrad": (_i32, [_PT, _vp, _f32, _vp]),
     "mke_rows_apply_adagrad_pair": (_i32, [_PT, _vp, _f32, _PT, _vp, _f32, _vp]),

@@ -29,6 +29,8 @@ static thread_local EventPool g_events[16];  // per device
 struct PhaseTimer {
   std::vector<cudaEvent_t> ev;  // pairs
   int used = 0;
+  int every = 1;  // time one launch in `every` (a timed event pair costs the step a few microseconds)
+  long long seen = 0;
 };
 static PhaseTimer g_timer;
 
@@ -131,7 +133,7 @@ extern "C" int mke_rel_train_steps(const mke_rel_view_t* v, int32_t first_step, 
     if (n > 0) {
       // ---- phase 1 ------------------------------------------------------------------------
       int rc;
-      const bool timed = g_timer.used + 2 <= (int)g_timer.ev.size();
+      const bool timed = g_timer.used + 2 <= (int)g_timer.ev.size() && (g_timer.seen++ % g_timer.every) == 0;
       if (timed) cudaEventRecord(g_timer.ev[g_timer.used], main);
       if (ahead)
         rc = mke_rel_step_structured2(v->ent, v->rel, c1, cur.len1, c2, cur.len2, v->K, v->neg_ent[s & 1],
@@ -193,6 +195,13 @@ extern "C" int mke_timing_enable(int32_t max_launches) {
   g_timer.used = 0;
   for (auto& e : g_timer.ev)
     if (cudaError_t err = cudaEventCreate(&e)) return cuda_fail(err, "cudaEventCreate");
+  return 0;
+}
+
+extern "C" int mke_timing_stride(int32_t every) {
+  MKE_CHECK_ARG(every >= 1, "every=%d", every);
+  g_timer.every = every;
+  g_timer.seen = 0;
   return 0;
 }
 
