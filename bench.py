@@ -11,7 +11,8 @@ synthetic with the measured degree laws), dim=75, batch=20 000, neg=10.
   e2e        same metric through the public step API with HOST (pinned) positives copied H2D and
              the batch loss read D2H every step
   roofline   phase-1 kernel: algorithmic bytes per launch / mean launch duration (CUDA events
-             around every phase-1 launch of the timed region) vs MEASURED_PEAKS.json hbm_gbs
+             around one phase-1 launch in --p1-every (default 4) of the timed region: a timed event
+             pair costs the step ~4 us, profiles/r1_bench_p1_every*.json) vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  oracle port of the reference CPU path on a bounded sample (rank 0, N=1)
 `--impl reference` times that CPU path alone and prints the same line shape.
 """
@@ -252,7 +253,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="draw negatives inside the fused kernel")
     ap.add_argument("--cpu-steps", type=int, default=8)
-    ap.add_argument("--p1-every", type=int, default=1,
+    ap.add_argument("--p1-every", type=int, default=4,
                     help="put the CUDA-event pair around one phase-1 launch in N of the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
