@@ -121,9 +121,19 @@ def main():
                         "elapsed_s": time.time() - t_start})
             print(json.dumps(log[-1]), flush=True)
         E = rv.ent.eval()
+        # the same metrics from the fused device evaluator (mke_sim_rank), candidates = the valid links'
+        # KG2 entities (base/evaluation.py valid()): must agree with the numpy/torch ranking below
+        from multike_b200 import similarity as S
+        rank, _ = S.sim_rank(rv.ent.var, rv.ent.var, idx1=valid[:, 0].astype(np.int32),
+                             idx2=valid[:, 1].astype(np.int32), normalize=True, dim=dim)
+        r = rank.cpu().numpy().astype(np.int64) + 1
+        device_eval = {"hits@%d" % k: float((r <= k).mean() * 100) for k in (1, 5, 10, 50)}
+        device_eval.update(mr=float(r.mean()), mrr=float((1.0 / r).mean()))
     res = hits(E[valid[:, 0]], E[valid[:, 1]])
     summary = {"impl": args.impl, "epochs": args.epochs, "batch": B, "neg": K, "valid_links": int(len(valid)),
                "train_seconds": time.time() - t_start, **res, "log": log}
+    if args.impl == "b200":
+        summary["device_evaluator"] = device_eval
     print(json.dumps({k: v for k, v in summary.items() if k != "log"}))
     if args.out:
         with open(args.out, "w") as fh:
