@@ -263,20 +263,14 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_tile_kernel(const SimParam
 // histogram) gives the key T of the k-th largest sim and how many columns equal to T belong to
 // the answer; the columns are then emitted in ASCENDING column order (all with key > T plus the
 // first `need_eq` with key == T), i.e. the list is deterministic where np.argpartition's is not.
-constexpr int kTopkThreads = 1024;
+constexpr int kTopkThreads = 256;
 constexpr int kTopkWarps = kTopkThreads / 32;
-constexpr int kTopkBins = 2048;
-// One 1024-thread block per SM: the 148 rows in flight (59 MB at 100 000 columns) stay in L2, so only
-// the first of the five sweeps over a row comes from HBM.
-constexpr size_t kTopkSmem = (size_t)kTopkWarps * kTopkBins * sizeof(uint16_t);
 
-__global__ void __launch_bounds__(kTopkThreads, 1) row_topk_kernel(const float* __restrict__ sims, size_t pitch, int n2,
-                                                                   int k, const int32_t* __restrict__ id_list,
-                                                                   int id_base, int32_t* __restrict__ out,
-                                                                   const int32_t* __restrict__ out_rows,
-                                                                   int row_base) {
-  extern __shared__ __align__(16) uint16_t s_wh[];  // [warp][bin]: warp-private counts of radix pass 0
-  __shared__ unsigned hist[kTopkBins];
+__global__ void __launch_bounds__(kTopkThreads) row_topk_kernel(const float* __restrict__ sims, size_t pitch, int n2,
+                                                                int k, const int32_t* __restrict__ id_list,
+                                                                int id_base, int32_t* __restrict__ out,
+                                                                const int32_t* __restrict__ out_rows, int row_base) {
+  __shared__ unsigned hist[2048];
   __shared__ unsigned s_bin, s_above;
   __shared__ int s_wg[kTopkWarps], s_we[kTopkWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -285,20 +279,13 @@ __global__ void __launch_bounds__(kTopkThreads, 1) row_topk_kernel(const float* 
   unsigned remaining = (unsigned)k;
   for (int pass = 0; pass < 3; ++pass) {
     const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-    const int nb = pass < 2 ? kTopkBins : 1024;
+    const int nb = pass < 2 ? 2048 : 1024;
     for (int b = tid; b < nb; b += kTopkThreads) hist[b] = 0u;
-    if (pass == 0) {
-      uint32_t* z = reinterpret_cast<uint32_t*>(s_wh);
-      for (int b = tid; b < kTopkWarps * kTopkBins / 2; b += kTopkThreads) z[b] = 0u;
-    }
     __syncthreads();
-    // Four consecutive columns per thread and trip (rows are 16-byte aligned and padded to a multiple
-    // of four floats; the pad is masked).  Pass 0 sees every column and only a handful of distinct
-    // bins (the top bits of sims in [-1, 1]): the lanes of a warp that share a bin are found with
-    // match.any and their leader bumps the warp's PRIVATE 16-bit counter -- a plain read-modify-write,
-    // no atomics, no traffic between warps.  Later passes see only the few columns of the threshold
-    // bin and use shared atomics.
-    volatile uint16_t* const mine = s_wh + warp * kTopkBins;
+    // four consecutive columns per thread and trip (rows are 16-byte aligned and padded to a
+    // multiple of four floats; the pad is masked).  Pass 0 sees every column and only a handful
+    // of distinct bins (the top bits of sims in [-1, 1]): one shared-memory atomic per warp and
+    // distinct bin (match.any).  Later passes see only the few columns of the threshold bin.
     for (int c0 = 0; c0 < n2; c0 += 4 * kTopkThreads) {
       const int c = c0 + 4 * tid;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -311,34 +298,24 @@ __global__ void __launch_bounds__(kTopkThreads, 1) row_topk_kernel(const float* 
         const unsigned bin = (key >> shift) & (unsigned)(nb - 1);
         if (pass == 0) {
           const unsigned peers = __match_any_sync(0xffffffffu, ok ? bin : 0xffffffffu);
-          if (ok && lane == __ffs(peers) - 1) mine[bin] = (uint16_t)(mine[bin] + __popc(peers));
-          __syncwarp();
+          if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
         } else if (ok) {
           atomicAdd(&hist[bin], 1u);
         }
       }
     }
     __syncthreads();
-    if (pass == 0) {
-      for (int b = tid; b < kTopkBins; b += kTopkThreads) {
-        unsigned t = 0u;
-#pragma unroll 8
-        for (int w = 0; w < kTopkWarps; ++w) t += s_wh[w * kTopkBins + b];
-        hist[b] = t;
-      }
-      __syncthreads();
-    }
     if (warp == 0) {
       // lane l owns bins [l * per, (l + 1) * per); suffix sums from the top bin down
       const int per = nb / 32;
-      unsigned own = 0u;
-      for (int b = 0; b < per; ++b) own += hist[lane * per + b];
+      unsigned mine = 0u;
+      for (int b = 0; b < per; ++b) mine += hist[lane * per + b];
       unsigned above = 0u;  // count in the bins of the lanes above this one
       for (int l = 31; l > 0; --l) {
-        const unsigned v = __shfl_sync(0xffffffffu, own, l);
+        const unsigned v = __shfl_sync(0xffffffffu, mine, l);
         if (l > lane) above += v;
       }
-      if (above < remaining && remaining <= above + own) {
+      if (above < remaining && remaining <= above + mine) {
         unsigned acc = above;
         for (int b = per - 1; b >= 0; --b) {
           const unsigned h = hist[lane * per + b];
@@ -499,16 +476,6 @@ extern "C" int mke_sim_topk(const float* emb, const int32_t* idx_or_null, int32_
   if (n == 0) return 0;
   MKE_CHECK_ARG(emb && workspace && neighbours_out, "null pointer");
   MKE_CHECK_ARG(k >= 1 && k <= n, "k=%d outside [1, n=%d]", k, n);
-  MKE_CHECK_ARG(n < 65536 * kTopkWarps, "n=%d: the select kernel counts a warp's share of a row in 16 bits", n);
-  {
-    static bool configured = false;
-    if (!configured) {
-      if (cudaError_t e = cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)kTopkSmem))
-        return cuda_fail(e, "cudaFuncSetAttribute(row_topk_kernel)");
-      configured = true;
-    }
-  }
   MKE_CHECK_ARG(dim > 0 && dim <= stride && sim_ws(dim) <= kSimMaxWs, "dim=%d outside (0,%d] or > stride=%d", dim,
                 kSimMaxWs, stride);
   MKE_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "workspace must be 16-byte aligned");
@@ -537,8 +504,8 @@ extern "C" int mke_sim_topk(const float* emb, const int32_t* idx_or_null, int32_
     p.out = sims;
     p.out_pitch = pitch;
     if (int rc = launch_sim_tiles<false>(p, stream)) return rc;
-    row_topk_kernel<<<rows, kTopkThreads, kTopkSmem, stream>>>(sims, pitch, n, k, id_list_or_null, id_base,
-                                                                neighbours_out, out_rows_or_null, r0);
+    row_topk_kernel<<<rows, kTopkThreads, 0, stream>>>(sims, pitch, n, k, id_list_or_null, id_base, neighbours_out,
+                                                        out_rows_or_null, r0);
     MKE_CHECK_LAUNCH("row_topk_kernel");
   }
   return 0;

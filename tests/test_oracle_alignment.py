@@ -38,3 +38,18 @@ def test_stable_tie_rule():
     assert rank.tolist() == [2, 3] and top1.tolist() == [1, 0]
     rank, _ = oa.gold_ranks(s, gold=np.array([0, 0]))
     assert rank.tolist() == [1, 0]
+
+
+def test_host_side_metrics_from_ranks_match_calculate_rank(ref):
+    """refapi.base.alignment.rank_metrics (the host arithmetic after mke_sim_rank) == the sums of
+    calculate_rank (base/alignment.py:141-163) on the reference's own cases"""
+    import torch
+    from multike_b200.refapi.base.alignment import rank_metrics
+    top_k = ref["top_k"].tolist()
+    for c in range(len(ref["align_cases"])):
+        a, b = ref["align%d_a" % c], ref["align%d_b" % c]
+        rank, _ = oa.gold_ranks(oa.sim(a, b, normalize=True))
+        mr, mrr, hits = rank_metrics(torch.from_numpy(rank), top_k)
+        assert hits == [float(x) for x in ref["align%d_hits" % c]]
+        assert mr == pytest.approx(float(ref["align%d_mr" % c]), rel=1e-12)
+        assert mrr == pytest.approx(float(ref["align%d_mrr" % c]), rel=1e-12)
