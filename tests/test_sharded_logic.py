@@ -150,3 +150,88 @@ def test_two_ranks_equal_one_process_on_the_whole_batch(tmp_path):
     assert got["loss"] == pytest.approx(loss, rel=1e-12)
     np.testing.assert_allclose(got["ent"], ent.var.numpy(), rtol=0, atol=1e-13)
     np.testing.assert_allclose(got["rel"], rel.var.numpy(), rtol=0, atol=1e-13)
+
+
+def _owner_worker(rank, world, port, golden_path, out):
+    """world-4 gloo emulation of "negatives where they live" with the ORACLE: every rank walks its
+    KG's whole slice (group_parts), keeps the negatives whose corrupted entity it owns (shard_owner,
+    KG-block placement) and the positive terms of its own range; dense gradients are all-reduced."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multike_b200.sharded import group_parts, shard_owner
+    from oracle import device_sampler as ds
+    from oracle import relation_view as orv
+    g = dict(np.load(golden_path))
+    n_ent = int(g["n_ent"])
+    t1, t2 = g["triples1"], g["triples2"]
+    all1, all2 = np.concatenate([t1, g["sup1"]]), np.concatenate([t2, g["sup2"]])
+    kg1 = ds.KG(entity_base=0, n_entities=n_ent, triples=all1)
+    kg2 = ds.KG(entity_base=n_ent, n_entities=n_ent, triples=all2)
+    gen = torch.Generator().manual_seed(1)
+    ent0 = torch.randn(2 * n_ent, 16, generator=gen, dtype=torch.float64) * 0.1
+    rel0 = torch.randn(5, 16, generator=gen, dtype=torch.float64) * 0.1
+    ent, rel = orv.DenseTable(ent0, True, torch.float64), orv.DenseTable(rel0, True, torch.float64)
+    K, per_rank, seed = 5, 30, 9
+    for step in range(3):
+        kg_no, (a, ln), (lo, hi), base = group_parts(len(t1), len(t2), per_rank * world, step, rank, world)
+        pos = (t1 if kg_no == 1 else t2)[a:a + ln]
+        kg = kg1 if kg_no == 1 else kg2
+        skey = ds.stream_key(seed, step)
+        neg = []
+        for i, (h, r, t) in enumerate(pos):
+            neg += ds.sample_one(kg, int(h), int(r), int(t), K, skey, base + i)
+        neg = np.asarray(neg).reshape(-1, 3)
+        pos_of_neg = np.repeat(np.arange(ln), K)
+        corrupted = np.where(neg[:, 0] != pos[pos_of_neg, 0], neg[:, 0], neg[:, 2])   # the replaced entity
+        same = (neg[:, 0] == pos[pos_of_neg, 0]) & (neg[:, 2] == pos[pos_of_neg, 2])  # negative == positive
+        corrupted = np.where(same, neg[:, 0], corrupted)
+        owner, _ = shard_owner(corrupted, world, split=n_ent)
+        mine = neg[owner == rank]
+        own_pos = pos[lo:hi]
+        loss, ge, gr = orv.relation_view_step(ent, rel, own_pos[:, 0], own_pos[:, 1], own_pos[:, 2], mine[:, 0],
+                                              mine[:, 1], mine[:, 2], 0.001, apply=False)
+        buf = torch.cat([ge.reshape(-1), gr.reshape(-1), torch.tensor([loss], dtype=torch.float64)])
+        dist.all_reduce(buf)
+        ge = buf[: ge.numel()].reshape(ge.shape)
+        gr = buf[ge.numel(): ge.numel() + gr.numel()].reshape(gr.shape)
+        from oracle.tf_semantics import adagrad_dense_
+        adagrad_dense_(ent.var, ent.acc("r"), ge, 0.001)
+        adagrad_dense_(rel.var, rel.acc("r"), gr, 0.001)
+    if rank == 0:
+        np.savez(out, ent=ent.var.numpy(), rel=rel.var.numpy(), loss=float(buf[-1]))
+    dist.destroy_process_group()
+
+
+def test_four_ranks_negatives_where_they_live_equal_one_process(tmp_path):
+    golden_path = os.path.join(ROOT, "tests", "golden", "ref_batch_relation.npz")
+    out = str(tmp_path / "four_ranks.npz")
+    world = 4
+    mp.spawn(_owner_worker, args=(world, _free_port(), golden_path, out), nprocs=world, join=True)
+    got = dict(np.load(out))
+    from oracle import device_sampler as ds
+    from oracle import relation_view as orv
+    from multike_b200.relation_view import clipped_slice, split_batch
+    g = dict(np.load(golden_path))
+    n_ent = int(g["n_ent"])
+    t1, t2 = g["triples1"], g["triples2"]
+    all1, all2 = np.concatenate([t1, g["sup1"]]), np.concatenate([t2, g["sup2"]])
+    kg1 = ds.KG(entity_base=0, n_entities=n_ent, triples=all1)
+    kg2 = ds.KG(entity_base=n_ent, n_entities=n_ent, triples=all2)
+    gen = torch.Generator().manual_seed(1)
+    ent0 = torch.randn(2 * n_ent, 16, generator=gen, dtype=torch.float64) * 0.1
+    rel0 = torch.randn(5, 16, generator=gen, dtype=torch.float64) * 0.1
+    ent, rel = orv.DenseTable(ent0, True, torch.float64), orv.DenseTable(rel0, True, torch.float64)
+    K, gb, seed = 5, 120, 9
+    for step in range(3):
+        b1, b2 = split_batch(len(t1), len(t2), gb)
+        a1, e1 = clipped_slice(len(t1), b1, step)
+        a2, e2 = clipped_slice(len(t2), b2, step)
+        p1, p2 = t1[a1:e1], t2[a2:e2]
+        neg = ds.sample_batch(p1, kg1, p2, kg2, K, seed, step)
+        pos = np.concatenate([p1, p2])
+        loss, _, _ = orv.relation_view_step(ent, rel, pos[:, 0], pos[:, 1], pos[:, 2], neg[:, 0], neg[:, 1], neg[:, 2],
+                                            0.001, slot="r")
+    assert got["loss"] == pytest.approx(loss, rel=1e-12)
+    np.testing.assert_allclose(got["ent"], ent.var.numpy(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(got["rel"], rel.var.numpy(), rtol=0, atol=1e-13)
