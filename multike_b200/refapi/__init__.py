@@ -1,7 +1,16 @@
 """Host-side mirror of the reference's operator surface for the hot path.
 
-``losses`` and ``MultiKE_model`` keep the public names, argument meaning and error behaviour of
-/root/reference/code/losses.py and /root/reference/code/MultiKE_model.py (relation-view part), with
-torch CUDA tensors / device tables in place of TF tensors.  To let the reference's own scripts
-import them under their original top-level names, put this directory first on ``sys.path``.
+Modules keep the public names, argument meaning and error behaviour of their counterparts under
+/root/reference/code, with torch CUDA tensors / device tables in place of TF tensors:
+
+  losses              losses.py (8 functions, differentiable)
+  MultiKE_model       class MultiKE: graphs, trainers, reads, save
+  MultiKE_CSL         MultiKE_CV (run_ITC.py)          -> drivers.py
+  MultiKE_Late        MultiKE_Late, valid/test[_WVA] (run_SSL.py) -> drivers.py
+  literal_encoder     AutoEncoderModel
+  base.evaluation / base.alignment / base.batch   valid/test, greedy_alignment, generate_neighbours
+
+To let the reference's own scripts import them under their original top-level names, put this
+directory first on ``sys.path``; `utils`, `data_model` and `predicate_alignment` stay the
+reference's own host-side modules.
 """
