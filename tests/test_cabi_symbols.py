@@ -47,3 +47,25 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_cabi.MkeTable) == 3 * 8 + 9 * 4 + 4 + 3 * 8 * 8
     assert ctypes.sizeof(_cabi.MkeTripleSet) == 16
     assert ctypes.sizeof(_cabi.MkeKgSampler) == 8 + 4 + 4 + 8 + 4 + 4 + 16
+
+
+def test_similarity_and_ownership_entry_points_validate_on_the_host():
+    """argument errors of the newer entry points are reported before any device work"""
+    lib = _cabi.load()
+    assert lib.mke_sim_rank_workspace_floats(10000, 70000, 75) == 80 * 80000 + 10000 + 2 * 10000 + 8
+    assert lib.mke_sim_rank_workspace_floats(-1, 5, 75) == -1
+    assert lib.mke_sim_topk_workspace_floats(100000, 75, 8192) == 100000 * 80 + 8192 * 100000 + 8
+    assert lib.mke_sim_rank(None, None, 5, None, None, 5, 80, 75, 1, None, None, None, None, None) == _cabi.MKE_EINVAL
+    assert b"null pointer" in lib.mke_last_error()
+    assert lib.mke_sim_rank(None, None, 0, None, None, 5, 80, 75, 1, None, None, None, None, None) == 0  # no rows: no-op
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p).value
+    assert lib.mke_sim_topk(p, None, 10, 80, 75, 0, 11, None, 0, None, p, 1 << 20, p, None) == _cabi.MKE_EINVAL
+    assert b"k=11" in lib.mke_last_error()
+    assert lib.mke_sim_topk(p, None, 10, 200, 150, 0, 3, None, 0, None, p, 1 << 20, p, None) == _cabi.MKE_EINVAL  # dim > 128
+    assert lib.mke_neg_keep_owned(p, 4, 10, 3, 0, 0, 0, p, None) == _cabi.MKE_EINVAL
+    assert b"n_shards=3" in lib.mke_last_error()
+    # the dummy row must live on the caller's shard (KG-block placement: KG2 starts at id 100)
+    assert lib.mke_neg_keep_owned(p, 4, 10, 4, 100, 3, 0, p, None) == _cabi.MKE_EINVAL
+    assert b"dummy row" in lib.mke_last_error()
+    assert lib.mke_timing_stride(0) == _cabi.MKE_EINVAL and lib.mke_timing_stride(4) == 0 and lib.mke_timing_stride(1) == 0
