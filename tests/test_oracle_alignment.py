@@ -53,3 +53,22 @@ def test_host_side_metrics_from_ranks_match_calculate_rank(ref):
         assert hits == [float(x) for x in ref["align%d_hits" % c]]
         assert mr == pytest.approx(float(ref["align%d_mr" % c]), rel=1e-12)
         assert mrr == pytest.approx(float(ref["align%d_mrr" % c]), rel=1e-12)
+
+
+def test_evaluation_entry_points_forward_to_greedy_alignment(monkeypatch):
+    """refapi.base.evaluation.valid / test (base/evaluation.py:6-28): argument order, defaults
+    (valid is the quick ranking, test the accurate one) and return shapes -- with the ranker
+    replaced by a recorder, so no device is needed."""
+    from multike_b200.refapi.base import evaluation as eva
+    calls = []
+
+    def fake(embed1, embed2, top_k, nums_threads, metric, normalize, csls_k, accurate):
+        calls.append((embed1, embed2, top_k, nums_threads, metric, normalize, csls_k, accurate))
+        return {(0, 1)}, 12.5, 3.0, 0.25
+
+    monkeypatch.setattr(eva, "greedy_alignment", fake)
+    assert eva.valid("A", "B", None, [1, 5], 8, normalize=True) == (12.5, 0.25)
+    assert calls[-1] == ("A", "B", [1, 5], 8, "inner", True, 0, False)
+    assert eva.test("A", "B", None, [1], 4) == ({(0, 1)}, 12.5, 0.25)
+    assert calls[-1] == ("A", "B", [1], 4, "inner", False, 0, True)
+    assert eva.early_stop(0.5, 0.4, 0.3) == (0.4, 0.3, True) and eva.early_stop(0.3, 0.4, 0.5) == (0.4, 0.5, False)
