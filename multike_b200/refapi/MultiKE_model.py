@@ -32,6 +32,16 @@ def generate_out_folder(out_folder, training_data_path, div_path, method_name):
     return folder
 
 
+def write_id_dict(path, dic):
+    """utils.dict2file (utils.py:60-67): one "key<TAB>id" line per entry; None writes nothing"""
+    if dic is None:
+        return
+    with open(path, 'w', encoding='utf8') as f:
+        for key, idx in dic.items():
+            f.write(str(key) + '\t' + str(idx) + '\n')
+    print(path, "saved.")
+
+
 def _triples(lst, with_weight=False):
     a = np.asarray(lst, dtype=np.float64 if with_weight else np.int64)
     if a.size == 0:
@@ -323,6 +333,10 @@ class MultiKE:
                            ("rel_embeds", self.rel_embeds), ("attr_embeds", self.attr_embeds)):
             if tab is not None:
                 np.save(folder + fname + '.npy', tab.eval())
+        # the id dictionaries next to them: "<key>\t<id>" per line (utils.py:60-67, :84-89)
+        for kg_name, kg in (("kg1", self.kgs.kg1), ("kg2", self.kgs.kg2)):
+            for what, attr in (("ent", "entities_id_dict"), ("rel", "relations_id_dict"), ("attr", "attributes_id_dict")):
+                write_id_dict(folder + kg_name + '_' + what + '_ids', getattr(kg, attr, None))
         print("Embeddings saved!")
 
     # --- training (MultiKE_model.py:291-317) ---------------------------------------------------

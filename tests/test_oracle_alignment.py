@@ -72,3 +72,14 @@ def test_evaluation_entry_points_forward_to_greedy_alignment(monkeypatch):
     assert eva.test("A", "B", None, [1], 4) == ({(0, 1)}, 12.5, 0.25)
     assert calls[-1] == ("A", "B", [1], 4, "inner", False, 0, True)
     assert eva.early_stop(0.5, 0.4, 0.3) == (0.4, 0.3, True) and eva.early_stop(0.3, 0.4, 0.5) == (0.4, 0.5, False)
+
+
+def test_id_dict_files_have_the_reference_format(tmp_path, capsys):
+    """MultiKE.save's id dictionaries (utils.py:60-67): "key<TAB>id" lines; a missing dict writes no file"""
+    from multike_b200.refapi.MultiKE_model import write_id_dict
+    path = str(tmp_path / "kg1_ent_ids")
+    write_id_dict(path, {"http://dbpedia.org/resource/A": 0, "http://dbpedia.org/resource/B": 7})
+    assert open(path, encoding="utf8").read() == "http://dbpedia.org/resource/A\t0\nhttp://dbpedia.org/resource/B\t7\n"
+    assert "saved." in capsys.readouterr().out
+    write_id_dict(str(tmp_path / "none"), None)
+    assert not (tmp_path / "none").exists()
