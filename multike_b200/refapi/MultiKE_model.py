@@ -11,6 +11,11 @@ kernels of csrc/mke_cnn.cu, and ITC common-space learning (:225-239, :458-473) o
 alignment kernel, and SSL space mapping (:241-261, :439-454; its 75x75 products go through
 cuBLAS, gradient rows and Adagrad through the kernels).
 """
+import sys as _sys
+
+if __name__ == "MultiKE_model":  # imported under the reference's top-level name (refapi first on sys.path):
+    import multike_b200.refapi.MultiKE_model as _canonical  # one module object, whichever name imported it first
+    _sys.modules[__name__] = _canonical
 import math
 import os
 import time

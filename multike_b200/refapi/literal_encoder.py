@@ -7,6 +7,11 @@ on the tensor cores through cuBLAS (torch.matmul, TF32 inputs / fp32 accumulate 
 vector whose Adagrad update is the hand-written dense kernel mke_dense_apply_adagrad
 (acc0 = 0.1, no epsilon [TF semantics]).  No CPU path.
 """
+import sys as _sys
+
+if __name__ == "literal_encoder":  # imported under the reference's top-level name (refapi first on sys.path):
+    import multike_b200.refapi.literal_encoder as _canonical  # one module object, whichever name imported it first
+    _sys.modules[__name__] = _canonical
 import time
 
 import numpy as np
@@ -139,3 +144,43 @@ class AutoEncoderModel:
             out[a:a + batch_size] = h.cpu().numpy()
         print("encoded literal embeddings", out.shape)
         return out
+
+
+# ---- the literal pipeline around the auto-encoder (code/literal_encoder.py:147-180) -----------------
+def generate_unlisted_word2vec(word2vec, literal_list):
+    """words of the literals that the word-vector table lacks get character-level vectors
+    (utils.generate_word2vec_by_character_embedding: a gensim Word2Vec over characters -- host code of
+    the reference, imported from its `utils` when there is anything to embed)"""
+    missing = [w for literal in literal_list for w in literal.split(' ') if w not in word2vec]
+    if missing:
+        from utils import generate_word2vec_by_character_embedding  # the reference's module (needs gensim)
+        word2vec.update(generate_word2vec_by_character_embedding(missing))
+    return word2vec
+
+
+def literal_token_matrix(literal_list, word2vec, tokens_max_len=5, word2vec_dimension=300):
+    """[L, tokens_max_len, dim] float32: the vectors of each literal's first tokens, zeros elsewhere"""
+    out = np.zeros((len(literal_list), tokens_max_len, word2vec_dimension), dtype=np.float32)
+    for row, literal in zip(out, literal_list):
+        for i, word in enumerate(literal.split(' ')[:tokens_max_len]):
+            vec = word2vec.get(word)
+            if vec is not None:
+                row[i] = vec
+    return out
+
+
+class LiteralEncoder:
+    """literals -> token vectors -> auto-encoder trained for args.encoder_epoch epochs -> codes
+    (`encoded_literal_vector`, float64 [L, args.dim]); what data_model.py:81-83 instantiates"""
+
+    def __init__(self, literal_list, word2vec, args, tokens_max_len=5, word2vec_dimension=300):
+        self.args = args
+        self.literal_list = literal_list
+        self.word2vec = generate_unlisted_word2vec(word2vec, literal_list)
+        self.tokens_max_len = tokens_max_len
+        self.word2vec_dimension = word2vec_dimension
+        tokens = literal_token_matrix(literal_list, self.word2vec, tokens_max_len, word2vec_dimension)
+        model = AutoEncoderModel(tokens, args, input_dimension=tokens_max_len * word2vec_dimension)
+        for epoch in range(1, args.encoder_epoch + 1):
+            model.train_one_epoch(epoch)
+        self.encoded_literal_vector = model.encoder_multi_batches(tokens)

@@ -7,6 +7,11 @@ pass) and are differentiable through torch.autograd.Function.  space_mapping_los
 (losses.py:53-63; 75x75 matmuls, SURVEY.md section 8 row a-14 = "next") use torch's cuBLAS matmul.
 There is no CPU path: CPU tensors raise.
 """
+import sys as _sys
+
+if __name__ == "losses":  # imported under the reference's top-level name (refapi first on sys.path):
+    import multike_b200.refapi.losses as _canonical  # one module object, whichever name imported it first
+    _sys.modules[__name__] = _canonical
 import torch
 
 from multike_b200 import _cabi

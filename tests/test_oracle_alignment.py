@@ -83,3 +83,22 @@ def test_id_dict_files_have_the_reference_format(tmp_path, capsys):
     assert "saved." in capsys.readouterr().out
     write_id_dict(str(tmp_path / "none"), None)
     assert not (tmp_path / "none").exists()
+
+
+def test_literal_token_matrix_matches_reference_loop():
+    """refapi.literal_encoder.literal_token_matrix == the per-literal loop of literal_encoder.py:166-172"""
+    from multike_b200.refapi.literal_encoder import generate_unlisted_word2vec, literal_token_matrix
+    rng = np.random.default_rng(0)
+    w2v = {w: rng.standard_normal(6).astype(np.float32) for w in ("new", "york", "city", "of", "x")}
+    lits = ["new york", "city of new york state capital", "unknown words", "x", ""]
+    got = literal_token_matrix(lits, w2v, tokens_max_len=5, word2vec_dimension=6)
+    want = []
+    for literal in lits:
+        vectors = np.zeros((5, 6), dtype=np.float32)
+        words = literal.split(' ')
+        for i in range(min(5, len(words))):
+            if words[i] in w2v:
+                vectors[i] = w2v[words[i]]
+        want.append(vectors)
+    assert np.array_equal(got, np.stack(want))
+    assert sorted(generate_unlisted_word2vec(dict(w2v), ["new york", "x"])) == sorted(w2v)   # nothing missing: no gensim needed
