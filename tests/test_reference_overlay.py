@@ -43,6 +43,13 @@ for name in ("train_relation_view_1epo", "train_attribute_view_1epo", "train_cro
              "train_cross_kg_attribute_inference_1epo", "train_shared_space_mapping_1epo",
              "train_common_space_learning_1epo", "eval_kg1_useful_ent_embeddings", "eval_kg2_useful_ent_embeddings", "save"):
     assert callable(getattr(MultiKE_model.MultiKE, name)), name
+import Levenshtein                                     # stand-in here; predicate_alignment.py:2
+assert abs(Levenshtein.ratio("kitten", "sitting") - 8 / 13) < 1e-12 and Levenshtein.ratio("", "") == 1.0
+assert Levenshtein.ratio("birthPlace", "birthPlace") == 1.0 and Levenshtein.ratio("abc", "xyz") == 0.0
+assert Levenshtein.distance("kitten", "sitting") == 3
+import predicate_alignment                            # run_ITC.py:5 -- the reference's PredicateAlignModel
+assert os.path.samefile(predicate_alignment.__file__, os.path.join(ref, "predicate_alignment.py"))
+assert callable(predicate_alignment.PredicateAlignModel)
 print("OVERLAY OK")
 '''
 
