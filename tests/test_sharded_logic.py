@@ -203,10 +203,12 @@ def _owner_worker(rank, world, port, golden_path, out):
     dist.destroy_process_group()
 
 
-def test_four_ranks_negatives_where_they_live_equal_one_process(tmp_path):
+@pytest.mark.parametrize("world", [4, 8])
+def test_ranks_negatives_where_they_live_equal_one_process(tmp_path, world):
+    """world 4: two ranks per KG; world 8: four ranks per KG and, with 240 positives per global step
+    over 700 + 500 triples, short and empty tail slices"""
     golden_path = os.path.join(ROOT, "tests", "golden", "ref_batch_relation.npz")
-    out = str(tmp_path / "four_ranks.npz")
-    world = 4
+    out = str(tmp_path / "ranks.npz")
     mp.spawn(_owner_worker, args=(world, _free_port(), golden_path, out), nprocs=world, join=True)
     got = dict(np.load(out))
     from oracle import device_sampler as ds
@@ -222,7 +224,7 @@ def test_four_ranks_negatives_where_they_live_equal_one_process(tmp_path):
     ent0 = torch.randn(2 * n_ent, 16, generator=gen, dtype=torch.float64) * 0.1
     rel0 = torch.randn(5, 16, generator=gen, dtype=torch.float64) * 0.1
     ent, rel = orv.DenseTable(ent0, True, torch.float64), orv.DenseTable(rel0, True, torch.float64)
-    K, gb, seed = 5, 120, 9
+    K, gb, seed = 5, 30 * world, 9
     for step in range(3):
         b1, b2 = split_batch(len(t1), len(t2), gb)
         a1, e1 = clipped_slice(len(t1), b1, step)
