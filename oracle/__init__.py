@@ -9,10 +9,20 @@ Pinning status (see DESIGN.md "Oracle"):
     reference's own ``code/base/batch.py`` and ``code/attr_batch.py`` run in the build container
     under fixed ``random``/``numpy`` seeds (fixtures in tests/golden/, generator
     tests/golden/make_golden.py).
-  * TF-1.x arithmetic (losses.py, l2_normalize, Adagrad; ``oracle/tf_semantics.py``,
+  * evaluator / neighbour search (``oracle/alignment.py``): PINNED -- equal to the outputs of the
+    reference's own ``code/base/alignment.py`` (greedy_alignment, calculate_rank) and
+    ``code/base/batch.py`` (find_neighbours) run in the build container (tests/golden/ref_sim.npz,
+    generator tests/golden/make_golden_sim.py); ties rank by ascending column (the reference leaves
+    that order to numpy's unstable sorts).
+  * device sampler (``oracle/device_sampler.py``): bit-exact restatement of the kernels' counter-based
+    sampler; its SEMANTICS (one coin per round, no replacement, filter, exactly K) are checked
+    against the pinned reference restatement statistically and case by case.
+  * TF-1.x arithmetic (losses.py, l2_normalize, Adagrad, conv(), the auto-encoder;
+    ``oracle/attr_cnn.py``, ``oracle/autoencoder.py``, ``oracle/tf_semantics.py``,
     ``oracle/relation_view.py``): PARITY UNPINNED -- TensorFlow 1.x is a third-party dependency
     that is neither vendored under /root/reference nor installable here (no wheel for Python
     3.12, no network) and the reference ships no tests or golden vectors.  The restatement follows
     the reference call sites line by line and TF's documented op semantics; its hand-derived
-    sparse form is cross-checked against torch autograd through the dense formulation.
+    sparse form is cross-checked against torch autograd through the dense formulation, and the
+    conv() restatement against an index-level numpy restatement (tests/test_oracle_attr_cnn.py).
 """
