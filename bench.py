@@ -136,7 +136,7 @@ def run_reference(args):
         return 0
     name = args.workload
     w = WORKLOADS[name]
-    steps = max(1, min(args.steps, 12))   # bounded sample: one step is ~0.5-1 s of all host cores
+    steps = max(1, min(args.steps, 60))   # bounded sample: one step is 0.13-0.45 s of all host cores (10-30 s in all)
     warmup = max(1, min(args.warmup, 2))
     r = cpu_baseline_run(name, steps, warmup)
     sample = "%d steps of batch %d (K=%d) of the same workload; sampler in %d forked processes + dense torch-CPU step" % (
@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("MKE_VARIANT", "3")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="draw negatives inside the fused kernel")
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the CPU baseline sample (0.13-0.45 s each)")
     ap.add_argument("--p1-every", type=int, default=4,
                     help="put the CUDA-event pair around one phase-1 launch in N of the timed region")
     args = ap.parse_args()
