@@ -55,3 +55,32 @@ def make_kgs(shape=None, seed=1234, **over):
     t2 = _one_kg(rng, half, cfg["n_ent"] - half, cfg["n_rel1"], cfg["n_rel"] - cfg["n_rel1"], cfg["n_triples2"])
     return dict(triples1=t1, triples2=t2, n_ent=cfg["n_ent"], n_rel=cfg["n_rel"], ent_split=half,
                 rel_split=cfg["n_rel1"])
+
+
+def _mix64(x):
+    """splitmix64 finaliser on uint64 arrays (the counter-based generator of csrc/mke_common.cuh)"""
+    x = x.copy()
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def literal_vectors(literal_ids, dim, seed=20190754):
+    """Stand-in for the literal / name embeddings when the authors' word-vector file is not available
+    (SURVEY.md section 8c "name view caveat"): literal i -> a unit vector of `dim` Gaussians that is a
+    pure function of (seed, i), so identical literals get identical vectors on every machine and the
+    tables never have to be stored.  float32 [len(literal_ids), dim]."""
+    ids = np.asarray(literal_ids, dtype=np.uint64).reshape(-1, 1)
+    cols = np.arange(dim, dtype=np.uint64).reshape(1, -1)
+    with np.errstate(over="ignore"):
+        key = (ids << np.uint64(20)) | cols
+        a = _mix64(key * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed))
+        b = _mix64(a + np.uint64(0x9E3779B97F4A7C15))
+    u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) * (1.0 / 9007199254740992.0)   # (0, 1]
+    u2 = (b >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    return z.astype(np.float32)
