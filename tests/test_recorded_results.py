@@ -17,3 +17,17 @@ def test_hits_within_half_a_point_of_the_oracle():
     for x, y in zip(o["log"], b["log"]):
         assert y["rel_loss"] == pytest.approx(x["rel_loss"], rel=1e-5)
         assert y["ckge_loss"] == pytest.approx(x["ckge_loss"], rel=1e-5)
+
+
+def test_multiview_oracle_record_is_complete():
+    """profiles/r1_multiview_oracle.json (tools/multiview_experiment.py --impl oracle): the target of the B200 arm"""
+    o = json.load(open(os.path.join(ROOT, "profiles", "r1_multiview_oracle.json")))
+    assert o["impl"] == "oracle" and o["epochs"] == len(o["log"]) >= 3 and o["candidates"] == 70000
+    rel = json.load(open(os.path.join(ROOT, "profiles", "r1_hits_oracle.json")))
+    # same relation-view inputs and negatives as the relation-only record: epoch 1 agrees
+    assert o["log"][0]["rel_loss"] == pytest.approx(rel["log"][0]["rel_loss"], rel=1e-6)
+    assert o["log"][0]["ckge_rel_loss"] == pytest.approx(rel["log"][0]["ckge_loss"], rel=1e-6)
+    for a, b in zip(o["log"], o["log"][1:]):
+        assert b["common_loss"] < a["common_loss"] and b["attr_loss"] < a["attr_loss"]
+    assert o["views"]["nv"]["hits@1"] == pytest.approx(64.83, abs=0.2)      # links with identical names
+    assert set(o["views"]) == {"nv", "rv", "av", "final"}
