@@ -56,7 +56,12 @@ def main():
     ap.add_argument("--batch", type=int, default=5000)
     ap.add_argument("--neg", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--mode", choices=["itc", "ssl"], default="itc",
+                    help="itc: MultiKE_CV epochs (common-space step every epoch); ssl: MultiKE_Late -- views only, "
+                         "then --shared-epochs of orthogonal space mapping (MultiKE_model.py:241-261, :439-454)")
+    ap.add_argument("--shared-epochs", type=int, default=10)
     args = ap.parse_args()
+    itc = args.mode == "itc"
     g = np.load(os.path.join(ROOT, "tests", "golden", "dbp_wd_100k_relation.npz"))
     mvw = np.load(os.path.join(ROOT, "tests", "golden", "dbp_wd_100k_multiview.npz"))
     from multike_b200 import synthetic
@@ -81,6 +86,12 @@ def main():
     init = {name: xavier_truncated_normal((rows, dim), gen) for name, rows in
             (("rv_ent", n_ent), ("rel", n_rel), ("av_ent", n_ent), ("attr", n_attr), ("ent", n_ent))}
     thetas = [oc.init_theta(dim, generator=torch.Generator().manual_seed(1000 + k)).float() for k in range(2)]
+    maps0 = []
+    mgen = torch.Generator().manual_seed(77)
+    for _ in range(3):   # tf.initializers.orthogonal(): QR of a normal matrix, signs fixed by diag(R)
+        qm, rm = torch.linalg.qr(torch.randn(dim, dim, generator=mgen))
+        maps0.append(qm * torch.sign(torch.diagonal(rm)))
+    maps0 = torch.stack(maps0).float().contiguous()   # name, relation, attribute view -> shared space
     rng = np.random.default_rng(99)   # list shuffles, cross-KG batches, entity batches: identical in both runs
     steps = -(-(len(t1) + len(t2)) // B)
     ck_steps = -(-len(sup) // B)
@@ -157,7 +168,7 @@ def main():
                 ck += attr_step(np.concatenate([P, np.ones((len(P), 1))], 1), 1, "ckge_attribute", False, 2.0)
             rec["ckge_attr_loss"] = ck / (cka_steps * B)
             cs = 0.0
-            for s in range(ent_steps):
+            for s in range(ent_steps if itc else 0):
                 idx = torch.as_tensor(rng.permutation(n_ent)[:B].astype(np.int64))
                 vs = [t.var.clone().requires_grad_(True) for t in (fin, ent, av)]
                 F, R, A = (l2_normalize(v, 1)[idx] for v in vs)
@@ -171,6 +182,25 @@ def main():
             rec["elapsed_s"] = time.time() - t_start
             log.append(rec)
             print(json.dumps(rec), flush=True)
+        if not itc:
+            from oracle import losses as ol
+            M, M_acc, eye = maps0.clone(), torch.full_like(maps0, 0.1), torch.eye(dim)
+            R_const, A_const = ent.view().detach(), av.view().detach()      # only "shared*" variables train (:257)
+            for epoch in range(1, args.shared_epochs + 1):
+                tot = 0.0
+                for s in range(ent_steps):
+                    idx = torch.as_tensor(rng.permutation(n_ent)[:B].astype(np.int64))
+                    v, m = fin.var.clone().requires_grad_(True), M.clone().requires_grad_(True)
+                    Fv = l2_normalize(v, 1)[idx]
+                    loss = sum(ol.space_mapping_loss(x[idx], Fv, m[k], eye, 2) for k, x in enumerate((N, R_const, A_const)))
+                    gv, gm = torch.autograd.grad(loss, [v, m])
+                    with torch.no_grad():
+                        adagrad_dense_(fin.var, fin.acc("shared_comb"), gv, lr)
+                        adagrad_dense_(M, M_acc, gm, lr)
+                    tot += float(loss)
+                rec = {"shared_epoch": epoch, "mapping_loss": tot / (ent_steps * B), "elapsed_s": time.time() - t_start}
+                log.append(rec)
+                print(json.dumps(rec), flush=True)
         tables = {"nv": names, "rv": ent.view().numpy(), "av": av.view().numpy(), "final": fin.view().numpy()}
     else:
         from multike_b200 import tables as T
@@ -228,7 +258,7 @@ def main():
                           "ckge_attribute", False, 2.0)
             rec["ckge_attr_loss"] = float(acc.item()) / (cka_steps * B)
             acc.zero_()
-            for s in range(ent_steps):
+            for s in range(ent_steps if itc else 0):
                 pick = torch.from_numpy(rng.permutation(n_ent)[:B].astype(np.int32)).cuda()
                 T.align_fwd_bwd(fin, N, rv.ent, av, pick, acc, name_weight=1.0, scale=1.0)
                 for t in (fin, rv.ent, av):
@@ -237,9 +267,37 @@ def main():
             rec["elapsed_s"] = time.time() - t_start
             log.append(rec)
             print(json.dumps(rec), flush=True)
+        if not itc:
+            from multike_b200 import _cabi
+            from multike_b200.refapi import losses as L
+            lib = _cabi.load()
+            M = maps0.cuda().contiguous()
+            M_grad, M_acc, eye = torch.zeros_like(M), torch.full_like(M, T.ADAGRAD_INIT), torch.eye(dim, device="cuda")
+            for epoch in range(1, args.shared_epochs + 1):
+                tot = torch.zeros((), dtype=torch.float64, device="cuda")
+                for s in range(ent_steps):
+                    idx = torch.from_numpy(rng.permutation(n_ent)[:B].astype(np.int32)).cuda()
+                    final = fin.export(idx).requires_grad_(True)
+                    views = (N.export(idx), rv.ent.export(idx), av.export(idx))
+                    m = M.detach().clone().requires_grad_(True)
+                    loss = sum(L.space_mapping_loss(x, final, m[k], eye, 2) for k, x in enumerate(views))
+                    g_final, g_m = torch.autograd.grad(loss, [final, m])
+                    fin.grad[:, :dim].index_add_(0, idx.long(), g_final)     # ids are distinct (random.sample)
+                    if fin.touched is not None:
+                        fin.touched[idx.long()] = 1
+                    fin.apply_adagrad("shared_comb", lr)
+                    M_grad.copy_(g_m)
+                    _cabi.check(lib.mke_dense_apply_adagrad(M.data_ptr(), M_grad.data_ptr(), M_acc.data_ptr(), M.numel(),
+                                                            float(lr), _cabi.current_stream()))
+                    tot += loss.detach().double()
+                rec = {"shared_epoch": epoch, "mapping_loss": float(tot) / (ent_steps * B), "elapsed_s": time.time() - t_start}
+                log.append(rec)
+                print(json.dumps(rec), flush=True)
         tables = {"nv": names, "rv": rv.ent.eval(), "av": av.eval(), "final": fin.eval()}
+    if not itc:   # MultiKE_Late.valid(embed_choice='avg'): the sum of the three (normalised) views
+        tables["avg"] = tables["nv"] + tables["rv"] + tables["av"]
     res = evaluate(tables)
-    summary = {"impl": args.impl, "epochs": args.epochs, "batch": B, "neg": K, "valid_links": int(len(valid)),
+    summary = {"impl": args.impl, "mode": args.mode, "shared_epochs": 0 if itc else args.shared_epochs, "epochs": args.epochs, "batch": B, "neg": K, "valid_links": int(len(valid)),
                "candidates": int(len(cand2)), "train_seconds": time.time() - t_start, "views": res, "log": log}
     print(json.dumps({k: v for k, v in summary.items() if k != "log"}))
     if args.out:
