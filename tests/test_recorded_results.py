@@ -31,3 +31,16 @@ def test_multiview_oracle_record_is_complete():
         assert b["common_loss"] < a["common_loss"] and b["attr_loss"] < a["attr_loss"]
     assert o["views"]["nv"]["hits@1"] == pytest.approx(64.83, abs=0.2)      # links with identical names
     assert set(o["views"]) == {"nv", "rv", "av", "final"}
+
+
+def test_multiview_ssl_oracle_record_is_complete():
+    o = json.load(open(os.path.join(ROOT, "profiles", "r1_multiview_ssl_oracle.json")))
+    assert o["impl"] == "oracle" and o["mode"] == "ssl" and set(o["views"]) == {"nv", "rv", "av", "avg", "final"}
+    views = [r for r in o["log"] if "epoch" in r]
+    maps = [r for r in o["log"] if "shared_epoch" in r]
+    assert len(views) == o["epochs"] and len(maps) == o["shared_epochs"] and all(r["common_loss"] == 0.0 for r in views)
+    assert all(b["mapping_loss"] < a["mapping_loss"] for a, b in zip(maps, maps[1:]))
+    itc = json.load(open(os.path.join(ROOT, "profiles", "r1_multiview_oracle.json")))
+    # the first epoch does not depend on the schedule (the common-space step comes last)
+    for k in ("rel_loss", "ckge_rel_loss", "attr_loss", "ckge_attr_loss"):
+        assert views[0][k] == pytest.approx(itc["log"][0][k], rel=1e-6)
