@@ -11,12 +11,15 @@ from oracle.tf_semantics import l2_normalize
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("dim,B,weighted,scale", [(75, 257, True, 1.0), (75, 64, False, 2.0), (32, 50, True, 1.0)])
+# B = 5000 is args.json's attribute_batch_size: the 8-way split-batch reduction of the parameter gradient
+# (n >= 2048) and the multi-iteration grid-stride passes only run at that size
+@pytest.mark.parametrize("dim,B,weighted,scale", [(75, 257, True, 1.0), (75, 64, False, 2.0), (32, 50, True, 1.0),
+                                                  (75, 5000, True, 1.0), (75, 5000, False, 2.0), (75, 2048, True, 1.0)])
 def test_attr_cnn_step_matches_oracle(dim, B, weighted, scale):
     from multike_b200 import tables as T
     from multike_b200.attr_view import AttrCNN, param_layout
     rng = np.random.default_rng(dim + B)
-    n_ent, n_attr, n_val = 400, 30, 300
+    n_ent, n_attr, n_val = (400, 30, 300) if B < 1000 else (20000, 300, 6000)
     ent0 = rng.normal(0, 0.02, (n_ent, dim))
     att0 = rng.normal(0, 0.05, (n_attr, dim))
     val0 = rng.normal(0, 0.3, (n_val, dim))

@@ -27,3 +27,35 @@ def test_three_epochs_on_dbp_wd_match_the_oracle_log(tmp_path):
     for k in ("hits@1", "hits@5", "hits@10", "hits@50"):
         assert dev[k] == pytest.approx(got[k], abs=0.05)
     assert dev["mrr"] == pytest.approx(got["mrr"], rel=1e-3)
+
+
+def _multiview(tmp_path, mode, oracle_record):
+    """BASELINE.json configs[2]: the full multi-view epoch (relation, cross-KG relation, attribute CNN, cross-KG
+    attribute, common space / space mapping) on the real DBP-WD-100K digest, B200 arm vs the committed CPU-oracle record
+    of the same tool on identical inputs: per-epoch losses rel 1e-5, Hits@1/10 within 0.5 points for every view."""
+    out = str(tmp_path / "mv.json")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "multiview_experiment.py"), "--impl", "b200", "--epochs", "10",
+           "--out", out] + (["--mode", "ssl"] if mode == "ssl" else [])
+    subprocess.run(cmd, check=True, cwd=ROOT, timeout=900, stdout=subprocess.DEVNULL)
+    got = json.load(open(out))
+    want = json.load(open(os.path.join(ROOT, "profiles", oracle_record)))
+    assert got["epochs"] == want["epochs"] and got["batch"] == want["batch"] and len(got["log"]) == len(want["log"])
+    for g, w in zip(got["log"], want["log"]):
+        for key, val in w.items():
+            if key.endswith("loss"):
+                assert g[key] == pytest.approx(val, rel=1e-5, abs=1e-12), (key, g, w)
+    assert set(got["views"]) == set(want["views"])
+    for view, w in want["views"].items():
+        for k in ("hits@1", "hits@5", "hits@10", "hits@50"):
+            assert abs(got["views"][view][k] - w[k]) <= 0.5, (view, k, got["views"][view][k], w[k])
+    return got
+
+
+def test_multiview_itc_on_dbp_wd_matches_the_oracle_record(tmp_path):
+    got = _multiview(tmp_path, "itc", "r1_multiview_oracle.json")
+    assert got["views"]["final"]["hits@1"] > 60.0
+
+
+def test_multiview_ssl_on_dbp_wd_matches_the_oracle_record(tmp_path):
+    got = _multiview(tmp_path, "ssl", "r1_multiview_ssl_oracle.json")
+    assert got["views"]["avg"]["hits@1"] > 55.0
