@@ -38,7 +38,9 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "dwy100k_rel_d75_b20000_k10"
 FALLBACK_HBM_GBS = 6650.0
-P1_KERNEL = ["rel_fused_q8_kernel", "rel_fused_tma_kernel", "rel_fused_ldg_kernel", "rel_fused_q8p_kernel"]
+P1_KERNEL = ["rel_fused_q8_kernel", "rel_fused_tma_kernel", "rel_fused_ldg_kernel", "rel_fused_q8p_kernel",
+             "rel_step_persist_kernel"]
+VARIANT_NAME = ["q8_ldg_red", "tma_bulk", "warp_ldg_red", "q8_row_stream", "persistent_step_kernel"]
 
 
 def bytes_per_positive(dim, K):
@@ -46,14 +48,36 @@ def bytes_per_positive(dim, K):
     return 2 * (3 + K) * dim * 4 + 12
 
 
+def bytes_per_applied_row(dim):
+    """SURVEY.md 8(d), phase 2: read g, v, acc + write v, acc + re-zero g per touched row."""
+    return 6 * dim * 4
+
+
 def ncu_traffic(workload, kernel):
     """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
-            k = json.load(fh)[workload][kernel]
-        return k["dram_read_bytes"] + k["dram_write_bytes"]
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                k = json.load(fh)[workload][kernel]
+            return k["dram_read_bytes"] + k["dram_write_bytes"]
+        except Exception:
+            continue
+    return None
+
+
+def touched_rows_per_step(rv, steps=4):
+    """Distinct entity rows one step touches (its positives' endpoints and its negatives), averaged over a
+    few steps of the epoch, with the product's own sampler: the row count of phase 2."""
+    import torch
+    from multike_b200 import tables as T
+    tot = 0
+    for step in range(steps):
+        (a1, b1), (a2, b2) = rv.step_slices(step)
+        p1, p2 = rv.triples1[a1:b1], rv.triples2[a2:b2]
+        ne, _ = T.sample_structured(p1, rv.kg1, p2, rv.kg2, rv.K, rv.seed, step)
+        ids = torch.cat([p1[:, 0], p1[:, 2], p2[:, 0], p2[:, 2], ne.reshape(-1)])
+        tot += int(torch.unique(ids).numel())
+    return tot / steps
 
 
 def measured_peak():
@@ -301,8 +325,9 @@ def main():
     barrier()
     if rank == 0:
         clocks.start()
-    _cabi.check(lib.mke_timing_enable(args.steps))  # CUDA events around the phase-1 launches
-    _cabi.check(lib.mke_timing_stride(max(1, args.p1_every)))
+    persistent = args.variant == 4 and rv.persist_chunk > 0
+    _cabi.check(lib.mke_timing_enable(args.steps))  # CUDA events around the phase-1 (variant 4: all) launches
+    _cabi.check(lib.mke_timing_stride(1 if persistent else max(1, args.p1_every)))
     launches0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -317,6 +342,15 @@ def main():
     _cabi.check(lib.mke_timing_read(ctypes.byref(tot), ctypes.byref(cnt)))
     p1_ms = tot.value / max(cnt.value, 1)
     _cabi.check(lib.mke_timing_enable(0))
+    phases = None
+    if persistent:  # device-side stamps of the last launch: where the step's time goes inside the kernel
+        n_last = args.steps - (args.steps - 1) // rv.persist_chunk * rv.persist_chunk
+        st = rv.persist_trace(n_last).cpu().numpy().astype("float64")
+        d = st[2:] - st[1:-1]
+        phases = {"steps_in_last_launch": int(n_last), "prologue_us": (st[1] - st[0]) * 1e-3,
+                  "phase1_us": float(d[0::2].mean()) * 1e-3, "phase2_us": float(d[1::2].mean()) * 1e-3,
+                  "note": "%globaltimer at the grid barriers of the last launch (phase incl. its barrier)"}
+        touched = touched_rows_per_step(rv)
 
     # how much of a CUDA-event pair is not the kernel: the same pair around a one-row fill kernel
     probe = torch.zeros(8, device="cuda")
@@ -361,6 +395,19 @@ def main():
         peak, peak_kind = measured_peak()
         pos_per_launch = positives / world / args.steps  # per rank per phase-1 launch
         alg_bytes = pos_per_launch * bytes_per_positive(dim, K)
+        kernel_note = P1_KERNEL[args.variant] + " (phase 1)"
+        if persistent:
+            # one launch = `steps per launch` whole steps: phase 1 (bytes_per_positive) + phase 2 (6 dim 4 B per
+            # touched entity row and per relation row; the sampler's few MB are not counted)
+            p1_bytes = alg_bytes
+            p2_bytes = (touched + kgs["n_rel"]) * bytes_per_applied_row(dim)
+            steps_per_launch = args.steps / max(cnt.value, 1)
+            alg_bytes = (p1_bytes + p2_bytes) * steps_per_launch
+            kernel_note = "rel_step_persist_kernel (negatives + phase 1 + phase 2 of %.1f steps per launch)" % steps_per_launch
+            phases.update({"phase1_algorithmic_bytes": p1_bytes, "phase2_algorithmic_bytes": p2_bytes,
+                           "touched_entity_rows_per_step": touched,
+                           "phase1_frac_of_peak": p1_bytes / (phases["phase1_us"] * 1e-6) / 1e9 / peak,
+                           "phase2_frac_of_peak": p2_bytes / (phases["phase2_us"] * 1e-6) / 1e9 / peak})
         achieved = alg_bytes / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": positives / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -368,7 +415,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "entities": kgs["n_ent"], "relations": kgs["n_rel"],
                        "triples": int(rv.n1 + rv.n2), "dim": dim, "batch": B, "neg": K, "steps_per_epoch": spe,
-                       "variant": ["q8_ldg_red", "tma_bulk", "warp_ldg_red", "q8_row_stream"][args.variant],
+                       "variant": VARIANT_NAME[args.variant],
                        "l2": "no flush: step working set (var+grad+Adagrad slot of the entity table, %d MB) exceeds "
                              "the 126 MB L2 and each step touches a different random row set"
                              % (3 * kgs["n_ent"] * rv.ent.stride * 4 // 2 ** 20),
@@ -383,13 +430,15 @@ def main():
                          "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload, P1_KERNEL[args.variant]),
                          "traffic_note": "dram bytes per launch, ncu --set full (cold L2), profiles/r1_traffic.json",
-                         "algorithmic_bytes": alg_bytes, "kernel": P1_KERNEL[args.variant] + " (phase 1)",
+                         "algorithmic_bytes": alg_bytes, "kernel": kernel_note,
                          "peak_source": peak_kind, "launch_ms": p1_ms, "timed_launches": int(cnt.value),
                          "bytes_per_positive": bytes_per_positive(dim, K),
                          "event_pair_floor_ms": event_floor_ms,
                          "event_pair_floor_note": "median of the same CUDA-event pair around a one-row fill kernel: "
                                                   "the part of launch_ms that is launch/event latency, not kernel"},
         }
+        if phases is not None:
+            line["roofline"]["phases"] = phases
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_baseline_run(args.workload, args.cpu_steps, 1)
             line["cpu_baseline"] = {

@@ -68,6 +68,8 @@ class MkeRelView(_c.Structure):
         ("neg_ent", _c.c_void_p * 2), ("neg_side", _c.c_void_p * 2),
         ("step_loss", _c.c_void_p), ("host_step_loss", _c.c_void_p),
         ("variant", _c.c_int32),
+        ("persist_ws", _c.c_void_p), ("persist_ws_bytes", _c.c_int64),
+        ("persist_chunk", _c.c_int32), ("persist_flag_src", _c.c_void_p),
     ]
 
 
@@ -90,6 +92,7 @@ SIGNATURES = {
                                         _i32, _vp]),
     "mke_neg_keep_owned": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
+    "mke_rel_persist_workspace_bytes": (_c.c_int64, [_i32, _i32, _i32, _i32]),
     "mke_attr_cnn_param_count": (_c.c_int64, [_i32]),
     "mke_attr_cnn_workspace_floats": (_c.c_int64, [_i32, _i32]),
     "mke_attr_cnn_fwd_bwd": (_i32, [_PT, _PT, _PT, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),

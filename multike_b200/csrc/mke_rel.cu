@@ -559,7 +559,7 @@ static int launch_rel(RelStepParams& p, int variant, cudaStream_t stream) {
   return 0;
 }
 
-static void fill_tables(RelStepParams& p, const mke_table_t* ent, const mke_table_t* rel) {
+void fill_tables(RelStepParams& p, const mke_table_t* ent, const mke_table_t* rel) {
   p.ent_var = ent->var;
   p.ent_grad = ent->grad;
   p.ent_touched = ent->touched;

@@ -1,0 +1,45 @@
+// Persistent step kernel of the relation view: parameters shared by the kernel (mke_rel_persist.cu)
+// and the step driver (mke_epoch.cu).
+#pragma once
+#include "mke_apply.cuh"
+#include "mke_rel_q8p.cuh"
+
+namespace mke {
+
+// words of PersistParams::sync (uint32, zeroed before every launch)
+constexpr int kSyncBarrier = 0;   // arrivals of the grid barrier (monotonic)
+constexpr int kSyncError = 1;     // != 0: a bounded wait ran out (the kernel traps right after)
+constexpr int kSyncPrologue = 2;  // sampling queue of the launch's first step
+constexpr int kSyncQueues = 4;    // + 2 * (step & 1) + {0: apply queue, 1: sampling queue}
+constexpr int kSyncWords = 64;
+
+struct PersistParams {
+  // positives: device-resident lists (t1/t2, indexed by list position), or -- host fed -- staging
+  // buffers that hold step k of this launch at k * b1 * 3 (kg1) / k * b2 * 3 (kg2), valid once
+  // flags[k] == flag_value
+  const int32_t* t1;
+  const int32_t* t2;
+  const int32_t* st1;
+  const int32_t* st2;
+  const uint32_t* flags;
+  uint32_t flag_value;
+  int n1, n2, b1, b2;
+  int steps_per_epoch, first_step, n_steps;
+  uint64_t seed, first_global_step;
+  int32_t* neg_ent[2];
+  uint32_t* neg_side[2];
+  ApplyTable A, B;     // entity table, relation table (phase 2)
+  uint32_t* sync;      // kSyncWords words
+  double* step_loss;   // device, step s of this launch adds to step_loss[s]
+  double* host_loss;   // device-visible pinned host memory or NULL: step_loss[s] is stored there after phase 1
+  unsigned long long* trace;  // NULL or [2 * n_steps + 2] globaltimer stamps: start, then after each barrier
+  int samp_mod;        // every samp_mod-th warp starts phase 2 on the sampling queue (>= 1)
+  unsigned long long* block_trace;  // debug (MKE_PERSIST_BLOCKTRACE): [barrier][block][4] stamps, else NULL
+};
+
+// returns 1 when the launch shape has no instantiation (caller falls back to one launch per phase)
+int launch_rel_persist(const RelStepParams& p, const PersistParams& q, cudaStream_t stream);
+
+void fill_tables(RelStepParams& p, const mke_table_t* ent, const mke_table_t* rel);
+
+}  // namespace mke

@@ -41,7 +41,8 @@ class RelationView:
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size=5000, neg_num=10,
                  lr=0.001, seed=0, device="cuda", variant=3, ent_init=None, rel_init=None,
-                 filter1=None, filter2=None, generator=None, pipelined=True, entities1=None, entities2=None):
+                 filter1=None, filter2=None, generator=None, pipelined=True, entities1=None, entities2=None,
+                 persist_chunk=None):
         self._lib = _cabi.load()
         self.device = torch.device(device)
         self.dim, self.batch_size, self.K, self.lr = int(dim), int(batch_size), int(neg_num), float(lr)
@@ -79,6 +80,15 @@ class RelationView:
         self._host_loss = None
         self._host_triples = None
         self._stage = None
+        # variant 4: persistent step kernel -- one cooperative launch per `persist_chunk` steps
+        self._persist_ws = self._flag_src = None
+        self.persist_chunk = 0
+        if self.variant == 4 and self.pipelined:
+            self.persist_chunk = int(persist_chunk) if persist_chunk else min(self.triple_steps, 64)
+            nbytes = int(self._lib.mke_rel_persist_workspace_bytes(self.n1, self.n2, self.batch_size, self.persist_chunk))
+            assert nbytes > 0
+            self._persist_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._flag_src = torch.arange(256, dtype=torch.int32).pin_memory()
         self._view = _cabi.MkeRelView()
         self._fill_view()
 
@@ -106,6 +116,9 @@ class RelationView:
             v.neg_ent[k] = self._neg[k][0].data_ptr() if self._neg else None
             v.neg_side[k] = self._neg[k][1].data_ptr() if self._neg else None
         v.step_loss = self._step_loss.data_ptr()
+        if self._persist_ws is not None:
+            v.persist_ws, v.persist_ws_bytes = self._persist_ws.data_ptr(), self._persist_ws.numel()
+            v.persist_chunk, v.persist_flag_src = self.persist_chunk, self._flag_src.data_ptr()
 
     # -- bookkeeping of the reference drivers -------------------------------------------------
     @property
@@ -167,6 +180,14 @@ class RelationView:
         self.global_step += n_steps
         self._last_steps = n_steps
         return int(positives.value)
+
+    def persist_trace(self, n_steps=None):
+        """Device-side phase stamps of the LAST persistent launch (variant 4), in nanoseconds of
+        %globaltimer: tensor [2 * n + 2] = launch start, after the negatives of the first step, then
+        after phase 1 and after phase 2 of each of the launch's n steps."""
+        assert self._persist_ws is not None
+        n = self.persist_chunk if n_steps is None else int(n_steps)
+        return self._persist_ws[256: 256 + 8 * (2 * n + 2)].view(torch.int64).clone()
 
     @property
     def step_losses(self):
