@@ -290,10 +290,10 @@ typedef struct mke_rel_view {
   double* host_step_loss;          /* pinned host [>= n_steps] or NULL: step_loss[s] is copied
                                       here (async, 8 bytes) after every step                    */
   int32_t variant;                 /* phase-1 schedule; 4 = persistent step kernel (below)         */
-  /* variant 4: ONE cooperative launch per `persist_chunk` consecutive steps (negatives, phase 1,
+  /* variant 4: ONE cooperative launch per `persist_chunk` (<= 128) consecutive steps (negatives, phase 1,
    * phase 2 separated by grid barriers instead of launches).  persist_ws: device workspace of
-   * mke_rel_persist_workspace_bytes() bytes, zero-initialised once by the caller.  Its first 256 bytes
-   * are the barrier / queue words; at byte 256 the last launch leaves uint64 globaltimer stamps
+   * mke_rel_persist_workspace_bytes() bytes, zero-initialised once by the caller.  Its first 2048 bytes
+   * are the barrier / queue words; at byte 2048 the last launch leaves uint64 globaltimer stamps
    * [2 * steps + 2]: launch start, after the negatives of its first step, then after phase 1 and after
    * phase 2 of every step.  Host-fed steps additionally need persist_flag_src: 256 uint32 in pinned
    * host memory holding 0..255 (the source of the 4-byte "batch k has landed" copies).            */

@@ -151,16 +151,16 @@ __device__ __forceinline__ void apply_one_row(const ApplyTable& T, size_t off, b
   }
 }
 
-// One chunk of 32 flagged-row candidates: the warp reads 32 flag bytes, clears the set ones, then its four
-// quarters take four flagged rows at a time (flagged rows are compacted by ballot, so all quarters stay
+// One chunk of CH (32 or 16) flagged-row candidates: the warp reads CH flag bytes, clears the set ones, then its
+// four quarters take four flagged rows at a time (flagged rows are compacted by ballot, so all quarters stay
 // busy whatever the touched fraction is).
-template <int FPL>
+template <int FPL, int CH = 32>
 __device__ __forceinline__ void apply_flag_chunk(const ApplyTable& T, int base, int lane) {
   constexpr int stride = FPL * 8;
   const int sub = lane & 7;
   const int q = lane >> 3;
   const int my = base + lane;
-  const bool flag = (my < T.rows) && (T.touched[my] != 0);
+  const bool flag = (lane < CH) && (my < T.rows) && (T.touched[my] != 0);
   uint32_t m = __ballot_sync(kFullMask, flag);
   if (flag) T.touched[my] = 0;
   while (m) {  // warp-uniform

@@ -89,7 +89,7 @@ static unsigned g_persist_seq = 0;  // launch counter: the value a launch's batc
 static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n_steps, uint64_t first_global_step,
                                   bool host_fed, int64_t* positives_out, cudaStream_t main, cudaStream_t side) {
   const int chunk = v->persist_chunk;
-  if (chunk < 1 || v->persist_ws == nullptr || v->K < 1 || !v->neg_ent[0] || !v->neg_ent[1] || !v->neg_side[0] ||
+  if (chunk < 1 || chunk > kPersistMaxChunk || v->persist_ws == nullptr || v->K < 1 || !v->neg_ent[0] || !v->neg_ent[1] || !v->neg_side[0] ||
       !v->neg_side[1] || v->ent->n_shards > 1)
     return 1;
   if (host_fed && (v->persist_flag_src == nullptr || side == nullptr || side == main)) return 1;
@@ -124,8 +124,6 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
   q.B = apply_table(v->rel, v->rel_acc, v->lr);
   q.sync = (uint32_t*)(ws + L.sync);
   q.trace = (unsigned long long*)(ws + L.trace);
-  static const int samp_mod = getenv("MKE_PERSIST_SAMP_MOD") ? atoi(getenv("MKE_PERSIST_SAMP_MOD")) : 3;
-  q.samp_mod = samp_mod > 0 ? samp_mod : 1;
   double* host_loss_dev = nullptr;  // the pinned loss buffer as the device sees it
   if (v->host_step_loss != nullptr) {
     void* d = nullptr;
@@ -192,7 +190,7 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
     static const int bt_at = getenv("MKE_PERSIST_BLOCKTRACE_AT") ? atoi(getenv("MKE_PERSIST_BLOCKTRACE_AT")) : 3;
     static int bt_calls = 0;
     unsigned long long* bt_buf = nullptr;
-    const size_t bt_words = (size_t)(2 * len + 1) * sm_count() * 4;
+    const size_t bt_words = (size_t)(2 * len + 2) * sm_count() * 4;
     q.block_trace = nullptr;
     if (bt_path != nullptr && bt_calls++ == bt_at && cudaMalloc(&bt_buf, bt_words * 8) == cudaSuccess) {
       cudaMemsetAsync(bt_buf, 0, bt_words * 8, main);
@@ -204,7 +202,7 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
     if (bt_buf != nullptr) {
       cudaStreamSynchronize(main);
       std::vector<unsigned long long> host(bt_words + 2);
-      host[0] = (unsigned long long)(2 * len + 1);
+      host[0] = (unsigned long long)(2 * len + 2);
       host[1] = (unsigned long long)sm_count();
       cudaMemcpy(host.data() + 2, bt_buf, bt_words * 8, cudaMemcpyDeviceToHost);
       if (FILE* f = fopen(bt_path, "wb")) {

@@ -5,17 +5,21 @@
 // quarter of each launch is grid ramp-up, drain and tail, plus the gaps between launches and the
 // cross-stream fence of the sampler (profiles/r1_phase1_trace.md: 75 us of kernels in an 89-93 us step).
 // Here the SMs stay loaded; the step boundaries that Adagrad's non-linearity forces (sum, then apply)
-// are grid barriers (one atomic + one acquire poll per block, ~1 us) instead of launches:
+// are grid barriers instead of launches.  One block per SM, WARP-SPECIALISED:
 //
-//   prologue : negatives of step 0                                             | barrier
-//   step s   : phase 1 (row stream, mke_rel_q8p.cuh)                           | barrier
-//              phase 2 (flagged rows, mke_apply.cuh) || negatives of step s+1  | barrier
+//   W worker warps : phase 1 of step s (row stream, mke_rel_q8p.cuh) | barrier 1 | phase 2 of step s
+//                    (flagged rows by ticket, mke_apply.cuh), leftovers of the sampling queue | barrier 2
+//   S sampler warps: negatives of step s+1 (tickets of 4 positives) all through step s        | barrier 2
 //
-// Phase 2 is HBM-bound and sampling is latency-bound with a few MB of traffic, so they share the
-// SMs: two work queues (atomic tickets); every samp_mod-th warp starts on the sampling queue and
-// moves to the apply queue when it is empty, the other warps the other way round.  The barrier's
-// fence (MEMBAR.SC.GPU + CCTL.IVALL) is what makes the rows another SM updated in phase 2 visible
-// to this SM's L1-allocating cp.async in the next phase 1.
+// Sampling reads only the triple lists, the filter set and the counter-based RNG -- never a table -- so it
+// needs no ordering against the phases except its buffers: the negatives of step s+1 go to buffer (s+1)&1,
+// last read by phase 1 of step s-1, and must be complete when phase 1 of step s+1 starts (barrier 2 of step s,
+// at which a block arrives only when the sampling queue is drained).  It is latency-bound work with a few MB of
+// traffic; giving it warps of its own (instead of time slices of the workers: measured 58-66 us for phase 2
+// + sampling against 45 us for phase 2 alone) lets it hide under both phases.
+// A barrier = bar.sync of the participating warps, one fence + one atomic per block, then every warp polls
+// with RELAXED loads and fences once (MEMBAR.SC.GPU + CCTL.IVALL): that acquire is what makes the rows another
+// SM updated in phase 2 visible to this SM's L1-allocating cp.async in the next phase 1.
 // Host-fed steps: the batches arrive by cudaMemcpyAsync on another stream while the kernel runs;
 // flags[k] (a 4-byte copy issued after the batch copy) tells the kernel that step k has landed, and
 // the step loss is stored straight into pinned host memory.
@@ -51,28 +55,15 @@ __device__ __noinline__ void wait_failed(uint32_t* sync, uint32_t code) {
   __trap();
 }
 
-// All blocks of the (cooperative, hence co-resident) grid.  `round` counts this block's barriers.
-// bt (debug, may be NULL): four stamps of this block -- arrived, fenced, released, done.
-__device__ __forceinline__ void grid_barrier(uint32_t* sync, uint32_t& round, unsigned long long* bt) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ++round;
-    const uint32_t target = round * gridDim.x;
-    if (bt) bt[0] = gtimer_raw();
-    __threadfence();  // release: this block's writes and reductions (ordered before by bar.sync)
-    if (bt) bt[1] = gtimer_raw();
-    atomicAdd(sync + kSyncBarrier, 1u);
-    const unsigned long long t0 = gtimer_raw();
-    while (ld_acquire_u32(sync + kSyncBarrier) < target) {
-      if (gtimer_raw() - t0 > kWaitLimitNs) wait_failed(sync, 1u);
-    }
-    if (bt) bt[2] = gtimer_raw();
-    __threadfence();  // acquire + L1 invalidation for the whole SM
-    if (bt) bt[3] = gtimer_raw();
-  }
-  __syncthreads();
+// ---- grid barrier (all blocks of the cooperative, hence co-resident, grid): one arrival per block, every
+// warp waits on its own ----------------------------------------------------------------------------------
+// The poll of the barrier counter is a RELAXED load (an acquire load is followed by CCTL.IVALL each time);
+// the one acquire fence (+ L1 invalidation) comes after the poll succeeded.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-
 struct StepSlice {
   const int32_t* pos1;
   int len1;
@@ -125,16 +116,18 @@ __device__ __forceinline__ uint32_t take_ticket(uint32_t* ctr, int lane) {
   return __shfl_sync(kFull, v, 0);
 }
 
+// one ticket of the apply queue: kApplyChunk flag bytes (large tables) or four rows (tables without flags)
+constexpr int kApplyChunk = 16;
 template <int FPL>
 __device__ __forceinline__ void apply_item(const ApplyTable& T, int item, int lane) {
   if (T.touched != nullptr)
-    apply_flag_chunk<FPL>(T, item * 32, lane);
+    apply_flag_chunk<FPL, kApplyChunk>(T, item * kApplyChunk, lane);
   else
     apply_row4<FPL>(T, item * 4, lane);
 }
 __host__ __device__ __forceinline__ int apply_items(const ApplyTable& T) {
   if (T.rows <= 0) return 0;
-  return T.touched != nullptr ? (T.rows + 31) / 32 : (T.rows + 3) / 4;
+  return T.touched != nullptr ? (T.rows + kApplyChunk - 1) / kApplyChunk : (T.rows + 3) / 4;
 }
 
 // The three phase bodies are separate functions so that each gets its own register allocation (the
@@ -160,7 +153,7 @@ static __device__ __noinline__ void phase2_apply(const PersistParams& q, uint32_
   }
 }
 
-// negatives of step s of the launch (tickets of 4 positives), after its batch has landed (host fed)
+// Negatives of step s of the launch (tickets of 4 positives), after its batch has landed (host fed): drains the queue.
 static __device__ __noinline__ void sample_queue(const RelStepParams& p, const PersistParams& q, const int s,
                                                  const StepSlice sl, uint32_t* ctr, volatile int32_t* pick,
                                                  const int lane) {
@@ -186,103 +179,117 @@ static __device__ __noinline__ void sample_queue(const RelStepParams& p, const P
   }
 }
 
-template <int FPL, int D, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) __maxnreg__(ps_max_regs(WARPS))
+template <int FPL, int D, int W, int S>
+__global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S))
     rel_step_persist_kernel(const __grid_constant__ RelStepParams p, const __grid_constant__ PersistParams q) {
   using Ring = Stage<FPL, D>;
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  unsigned char* const s_ring = s_dyn;                                               // [WARPS][Ring::kBytes]
-  int32_t* const s_ids = reinterpret_cast<int32_t*>(s_dyn + WARPS * Ring::kBytes);  // [WARPS][4][2][kIdStride]
-  float* const s_loss = reinterpret_cast<float*>(s_ids + WARPS * kQPerWarp * 2 * kIdStride);  // [WARPS]
+  unsigned char* const s_ring = s_dyn;                                           // [W][Ring::kBytes]
+  int32_t* const s_ids = reinterpret_cast<int32_t*>(s_dyn + W * Ring::kBytes);  // [W + S][4][2][kIdStride]
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7;
   const int qi = lane >> 3;
   const int wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * WARPS + wib;
-  const int Q = gridDim.x * WARPS * kQPerWarp;
+  const bool sampler = wib >= W;
+  const int gw = blockIdx.x * W + wib;  // workers only
+  const int Q = gridDim.x * W * kQPerWarp;
   const int g = gw * kQPerWarp + qi;
-  unsigned char* const ring_w = s_ring + wib * Ring::kBytes;
   int32_t* const ids_q = s_ids + (wib * kQPerWarp + qi) * 2 * kIdStride;
-  volatile int32_t* const pick = ids_q;  // sampler scratch (phase 1 is not running then)
-  float* const rel_grad = rel_grad_replica(p);
+  volatile int32_t* const pick = ids_q;  // sampler scratch (a worker samples only while its row stream is idle)
   const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
-  uint32_t round = 0;
-  int stamp = 0;
-  auto barrier = [&]() {
-    unsigned long long* bt =
-        q.block_trace ? q.block_trace + ((size_t)stamp * gridDim.x + blockIdx.x) * 4 : nullptr;
-    grid_barrier(q.sync, round, bt);
-    ++stamp;
-    if (leader && q.trace != nullptr) q.trace[stamp] = gtimer_raw();
+  const bool tracer = threadIdx.x == 0 && q.block_trace != nullptr;  // debug: thread 0 of every block
+  uint32_t round = 0;  // barriers completed
+  auto bt = [&](int k) -> unsigned long long& { return q.block_trace[((size_t)round * gridDim.x + blockIdx.x) * 4 + k]; };
+  // One arrival and ONE poller per block (thread 0), between two bar.syncs of the warps that take part (all of
+  // them, or the workers): waiting warps sit in the hardware barrier and put no load on the L2 slice of the
+  // counter (every warp polling for itself was measured: +10 us per phase).
+  auto barrier = [&](bool workers_only) {
+    auto block_sync = [&]() {
+      if (workers_only)
+        asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+      else
+        __syncthreads();
+    };
+    block_sync();
+    if (threadIdx.x == 0) {
+      if (tracer) bt(0) = gtimer_raw();
+      __threadfence();  // release: the block's writes and reductions (ordered before by bar.sync)
+      atomicAdd(q.sync + kSyncBarrier, 1u);
+      if (tracer) bt(1) = gtimer_raw();
+      const uint32_t target = (round + 1) * gridDim.x;
+      const unsigned long long t0 = gtimer_raw();
+      while (ld_relaxed_u32(q.sync + kSyncBarrier) < target) {
+        __nanosleep(100);
+        if (gtimer_raw() - t0 > kWaitLimitNs) wait_failed(q.sync, 1u);
+      }
+      if (tracer) bt(2) = gtimer_raw();
+      __threadfence();  // acquire + L1 invalidation for the whole SM
+      if (tracer) bt(3) = gtimer_raw();
+    }
+    block_sync();
+    ++round;
+    if (leader && q.trace != nullptr) q.trace[round] = gtimer_raw();
   };
   if (leader && q.trace != nullptr) q.trace[0] = gtimer_raw();
+  const StepSlice none{nullptr, 0, nullptr, 0};
 
-  // ---- prologue: negatives of the first step -------------------------------------------------------
+  // ---- prologue: negatives of the first step, by everybody -------------------------------------------
   StepSlice cur = step_slice_dev(q, 0);
-  sample_queue(p, q, 0, cur, q.sync + kSyncPrologue, pick, lane);
-  barrier();
+  sample_queue(p, q, 0, cur, q.sync + kSyncQueues + 1, pick, lane);
+  barrier(false);
 
+  if (sampler) {
+#pragma unroll 1
+    for (int s = 0; s < q.n_steps; ++s) {
+      if (s + 1 < q.n_steps)
+        sample_queue(p, q, s + 1, step_slice_dev(q, s + 1), q.sync + kSyncQueues + 2 * (s + 1) + 1, pick, lane);
+      ++round;  // barrier 1 is the workers'
+      barrier(false);
+    }
+    return;
+  }
+
+  unsigned char* const ring_w = s_ring + wib * Ring::kBytes;
+  float* const rel_grad = rel_grad_replica(p);
   const int items_b = apply_items(q.B), items_all = items_b + apply_items(q.A);
 #pragma unroll 1
   for (int s = 0; s < q.n_steps; ++s) {
     const int n = cur.len1 + cur.len2;
+    const bool has_next = s + 1 < q.n_steps;
+    const StepSlice nxt = has_next ? step_slice_dev(q, s + 1) : none;
     // ---- phase 1 ---------------------------------------------------------------------------------
-    if (leader) {  // the queues of the step after this one (last used two barriers ago)
-      q.sync[kSyncQueues + 2 * ((s + 1) & 1)] = 0u;
-      q.sync[kSyncQueues + 2 * ((s + 1) & 1) + 1] = 0u;
-    }
     if (n > 0) {
       const int passes = (n + Q - 1) / Q;
       const StepBatch b{cur.pos1, cur.len1, cur.pos2, cur.len2, q.neg_ent[s & 1], q.neg_side[s & 1]};
       const float loss_local = phase1_rows<FPL, D>(p, b, passes, Q, g, ring_w, ids_q, rel_grad, lane);
       float v = (sub == 0) ? loss_local : 0.f;
       v = warp_sum(v);
-      if (lane == 0) s_loss[wib] = v;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double a = 0.0;
-#pragma unroll 1
-        for (int w = 0; w < WARPS; ++w) a += (double)s_loss[w];
-        if (a != 0.0) atomicAdd(q.step_loss + s, a);
-      }
+      if (lane == 0 && v != 0.f) atomicAdd(q.step_loss + s, (double)v);
     }
-    barrier();
+    barrier(true);
     if (leader && q.host_loss != nullptr && n > 0) {
       const double v = __ldcg(q.step_loss + s);
       *reinterpret_cast<volatile double*>(q.host_loss + s) = v;
     }
-    // ---- phase 2 || negatives of the next step -----------------------------------------------------
-    const bool has_next = s + 1 < q.n_steps;
-    StepSlice nxt{nullptr, 0, nullptr, 0};
-    if (has_next) nxt = step_slice_dev(q, s + 1);
-    uint32_t* const ctr_apply = q.sync + kSyncQueues + 2 * (s & 1);
-    uint32_t* const ctr_samp = ctr_apply + 1;
-    const bool sampler_first = (gw % q.samp_mod) == 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      if ((half == 0) == sampler_first) {
-        if (has_next) sample_queue(p, q, s + 1, nxt, ctr_samp, pick, lane);
-      } else if (n > 0) {
-        phase2_apply<FPL>(q, ctr_apply, items_b, items_all, lane);
-      }
-    }
-    barrier();
+    // ---- phase 2, then whatever the sampler warps have left of the next step's negatives --------------
+    if (n > 0) phase2_apply<FPL>(q, q.sync + kSyncQueues + 2 * s, items_b, items_all, lane);
+    if (has_next) sample_queue(p, q, s + 1, nxt, q.sync + kSyncQueues + 2 * (s + 1) + 1, pick, lane);
+    barrier(false);
     cur = nxt;
   }
 }
 
-template <int FPL, int D, int WARPS>
+template <int FPL, int D, int W, int S>
 static int launch_persist(const RelStepParams& p, const PersistParams& q, cudaStream_t stream) {
-  auto kern = rel_step_persist_kernel<FPL, D, WARPS>;
+  auto kern = rel_step_persist_kernel<FPL, D, W, S>;
   using Ring = Stage<FPL, D>;
-  constexpr size_t smem = (size_t)WARPS * Ring::kBytes + (size_t)WARPS * kQPerWarp * 2 * kIdStride * sizeof(int32_t) +
-                          WARPS * sizeof(float);
+  constexpr size_t smem = (size_t)W * Ring::kBytes + (size_t)(W + S) * kQPerWarp * 2 * kIdStride * sizeof(int32_t);
   static bool configured = false;
   if (!configured) {
     if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
       return cuda_fail(e, "cudaFuncSetAttribute(rel_step_persist_kernel)");
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (W + S) * 32, smem) != cudaSuccess || per_sm < 1) {
       set_error("rel_step_persist_kernel does not fit an SM (%zu bytes of shared memory)", smem);
       return MKE_EINVAL;
     }
@@ -294,10 +301,22 @@ static int launch_persist(const RelStepParams& p, const PersistParams& q, cudaSt
     if (v > 0 && v < blocks) blocks = v;
   }
   void* args[] = {(void*)&p, (void*)&q};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(blocks), dim3(WARPS * 32), args, smem, stream);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(blocks), dim3((W + S) * 32), args, smem, stream);
   count_launch();
   if (e != cudaSuccess) return cuda_fail(e, "rel_step_persist_kernel");
   return 0;
+}
+
+// workers + samplers per block: 20 warps at stride <= 80 (5 per scheduler: 96 registers each), 16 above
+template <int FPL, int D, int WARPS>
+static int launch_persist_split(const RelStepParams& p, const PersistParams& q, cudaStream_t stream) {
+  static const int samplers = getenv("MKE_PERSIST_SAMPLERS") ? atoi(getenv("MKE_PERSIST_SAMPLERS")) : 2;
+  switch (samplers) {
+    case 1: return launch_persist<FPL, D, WARPS - 1, 1>(p, q, stream);
+    case 3: return launch_persist<FPL, D, WARPS - 3, 3>(p, q, stream);
+    case 4: return launch_persist<FPL, D, WARPS - 4, 4>(p, q, stream);
+    default: return launch_persist<FPL, D, WARPS - 2, 2>(p, q, stream);
+  }
 }
 
 int launch_rel_persist(const RelStepParams& p, const PersistParams& q, cudaStream_t stream) {
@@ -308,13 +327,13 @@ int launch_rel_persist(const RelStepParams& p, const PersistParams& q, cudaStrea
   switch (p.stride) {
 #define MKE_PS_CASE(STRIDE, FPL, WARPS)                                 \
   case STRIDE:                                                          \
-    if (deep) return launch_persist<FPL, 6, WARPS>(p, q, stream);       \
-    return launch_persist<FPL, 4, WARPS>(p, q, stream);
-    MKE_PS_CASE(32, 4, 18)
-    MKE_PS_CASE(64, 8, 18)
-    MKE_PS_CASE(80, 10, 18)
-    MKE_PS_CASE(104, 13, 15)
-    MKE_PS_CASE(128, 16, 15)
+    if (deep) return launch_persist_split<FPL, 6, WARPS>(p, q, stream); \
+    return launch_persist_split<FPL, 4, WARPS>(p, q, stream);
+    MKE_PS_CASE(32, 4, 20)
+    MKE_PS_CASE(64, 8, 20)
+    MKE_PS_CASE(80, 10, 20)
+    MKE_PS_CASE(104, 13, 16)
+    MKE_PS_CASE(128, 16, 16)
 #undef MKE_PS_CASE
     default: return 1;
   }

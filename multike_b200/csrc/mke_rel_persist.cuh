@@ -7,11 +7,12 @@
 namespace mke {
 
 // words of PersistParams::sync (uint32, zeroed before every launch)
-constexpr int kSyncBarrier = 0;   // arrivals of the grid barrier (monotonic)
+constexpr int kPersistMaxChunk = 128;  // steps per launch at most
+constexpr int kSyncBarrier = 0;   // arrivals of the grid barrier (monotonic, one per block and barrier)
 constexpr int kSyncError = 1;     // != 0: a bounded wait ran out (the kernel traps right after)
-constexpr int kSyncPrologue = 2;  // sampling queue of the launch's first step
-constexpr int kSyncQueues = 4;    // + 2 * (step & 1) + {0: apply queue, 1: sampling queue}
-constexpr int kSyncWords = 64;
+constexpr int kSyncQueues = 64;   // (own cache lines, away from the polled barrier word) + 2 k + {0: apply queue of step k, 1: sampling queue of step k} of the launch
+constexpr int kSyncWords = 512;   // >= kSyncQueues + 2 (kPersistMaxChunk + 1)
+constexpr int kSyncBytes = kSyncWords * 4;
 
 struct PersistParams {
   // positives: device-resident lists (t1/t2, indexed by list position), or -- host fed -- staging
@@ -33,8 +34,7 @@ struct PersistParams {
   double* step_loss;   // device, step s of this launch adds to step_loss[s]
   double* host_loss;   // device-visible pinned host memory or NULL: step_loss[s] is stored there after phase 1
   unsigned long long* trace;  // NULL or [2 * n_steps + 2] globaltimer stamps: start, then after each barrier
-  int samp_mod;        // every samp_mod-th warp starts phase 2 on the sampling queue (>= 1)
-  unsigned long long* block_trace;  // debug (MKE_PERSIST_BLOCKTRACE): [barrier][block][4] stamps, else NULL
+  unsigned long long* block_trace;  // debug (MKE_PERSIST_BLOCKTRACE): [barrier][block][4] stamps of warp 0: arrive, fenced, filler done, released, else NULL
 };
 
 // returns 1 when the launch shape has no instantiation (caller falls back to one launch per phase)

@@ -84,7 +84,7 @@ class RelationView:
         self._persist_ws = self._flag_src = None
         self.persist_chunk = 0
         if self.variant == 4 and self.pipelined:
-            self.persist_chunk = int(persist_chunk) if persist_chunk else min(self.triple_steps, 64)
+            self.persist_chunk = min(int(persist_chunk) if persist_chunk else self.triple_steps, 128)
             nbytes = int(self._lib.mke_rel_persist_workspace_bytes(self.n1, self.n2, self.batch_size, self.persist_chunk))
             assert nbytes > 0
             self._persist_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
@@ -187,7 +187,7 @@ class RelationView:
         after phase 1 and after phase 2 of each of the launch's n steps."""
         assert self._persist_ws is not None
         n = self.persist_chunk if n_steps is None else int(n_steps)
-        return self._persist_ws[256: 256 + 8 * (2 * n + 2)].view(torch.int64).clone()
+        return self._persist_ws[2048: 2048 + 8 * (2 * n + 2)].view(torch.int64).clone()
 
     @property
     def step_losses(self):
