@@ -137,7 +137,10 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or (_build._nvcc() and not _build.is_fresh()):
+    override = os.environ.get("MKE_LIB_OVERRIDE")  # development only: A/B two builds on one GPU box
+    if override:
+        path = override
+    elif not os.path.exists(path) or (_build._nvcc() and not _build.is_fresh()):
         path = _build.build()
     if not os.path.exists(path):
         raise RuntimeError("multike_b200: CUDA library %s is missing (run __graft_entry__.build())" % path)

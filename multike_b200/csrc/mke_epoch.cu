@@ -124,6 +124,15 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
   q.B = apply_table(v->rel, v->rel_acc, v->lr);
   q.sync = (uint32_t*)(ws + L.sync);
   q.trace = (unsigned long long*)(ws + L.trace);
+  static const int apply_mode = getenv("MKE_PERSIST_APPLY") ? atoi(getenv("MKE_PERSIST_APPLY")) : 1;
+  static const int apply_chunk = getenv("MKE_PERSIST_CHUNK") ? atoi(getenv("MKE_PERSIST_CHUNK")) : 32;
+  static const int samp_phase = getenv("MKE_PERSIST_SAMP_PHASE") ? atoi(getenv("MKE_PERSIST_SAMP_PHASE")) : 1;
+  q.samp_phase = samp_phase;
+  static const int fence_mode = getenv("MKE_PERSIST_FENCE") ? atoi(getenv("MKE_PERSIST_FENCE")) : 0;
+  q.fence_mode = fence_mode;
+
+  q.apply_mode = apply_mode;
+  q.apply_chunk = apply_chunk == 32 ? 32 : 16;
   double* host_loss_dev = nullptr;  // the pinned loss buffer as the device sees it
   if (v->host_step_loss != nullptr) {
     void* d = nullptr;

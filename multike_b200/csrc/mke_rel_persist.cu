@@ -5,24 +5,31 @@
 // quarter of each launch is grid ramp-up, drain and tail, plus the gaps between launches and the
 // cross-stream fence of the sampler (profiles/r1_phase1_trace.md: 75 us of kernels in an 89-93 us step).
 // Here the SMs stay loaded; the step boundaries that Adagrad's non-linearity forces (sum, then apply)
-// are grid barriers instead of launches.  One block per SM, WARP-SPECIALISED:
+// are grid barriers instead of launches.  One block of W warps per SM (default: all of them workers):
 //
-//   W worker warps : phase 1 of step s (row stream, mke_rel_q8p.cuh) | barrier 1 | phase 2 of step s
-//                    (flagged rows by ticket, mke_apply.cuh), leftovers of the sampling queue | barrier 2
-//   S sampler warps: negatives of step s+1 (tickets of 4 positives) all through step s        | barrier 2
+//   prologue : negatives of step 0 (tickets of 4 positives)                                 | barrier
+//   step s   : phase 1 = row stream of mke_rel_q8p.cuh, static split                       | barrier 1
+//              phase 2 = flagged rows as a second cp.async row stream (ApplyStream), by ticket,
+//              then the negatives of step s+1 (sampling reads no table)                    | barrier 2
 //
-// Sampling reads only the triple lists, the filter set and the counter-based RNG -- never a table -- so it
-// needs no ordering against the phases except its buffers: the negatives of step s+1 go to buffer (s+1)&1,
-// last read by phase 1 of step s-1, and must be complete when phase 1 of step s+1 starts (barrier 2 of step s,
-// at which a block arrives only when the sampling queue is drained).  It is latency-bound work with a few MB of
-// traffic; giving it warps of its own (instead of time slices of the workers: measured 58-66 us for phase 2
-// + sampling against 45 us for phase 2 alone) lets it hide under both phases.
-// A barrier = bar.sync of the participating warps, one fence + one atomic per block, then every warp polls
-// with RELAXED loads and fences once (MEMBAR.SC.GPU + CCTL.IVALL): that acquire is what makes the rows another
-// SM updated in phase 2 visible to this SM's L1-allocating cp.async in the next phase 1.
-// Host-fed steps: the batches arrive by cudaMemcpyAsync on another stream while the kernel runs;
-// flags[k] (a 4-byte copy issued after the batch copy) tells the kernel that step k has landed, and
-// the step loss is stored straight into pinned host memory.
+// A barrier = bar.sync, one fence + one atomic + ONE poller per block (relaxed loads), one fence
+// (MEMBAR.SC.GPU + CCTL.IVALL), bar.sync; about 1.5 us.  That acquire is what makes the rows another SM updated
+// in phase 2 visible to this SM's L1-allocating cp.async in the next phase 1.
+// Host-fed steps: the batches arrive by cudaMemcpyAsync on another stream while the kernel runs; flags[k] (a
+// 4-byte copy issued after the batch copy) tells the kernel that step k has landed, and the step loss is stored
+// straight into pinned host memory: the end-to-end rate equals the device-resident one.
+//
+// Measured on the way (B200, cfg 2, us per step; profiles/r2_persistent_kernel.md):
+//   * every warp arriving / polling for itself: fences of 2-7 us each while the SM still has reductions in flight,
+//     and +10 us per phase from the load on the counter's L2 slice -> one arrival and one poller per block;
+//   * warps specialised on sampling (MKE_PERSIST_SPLIT, kept as an experiment): 2 extra warps cost phase 1 4-5 us
+//     even when they sit idle in the hardware barrier, and phase 2 gains nothing;
+//   * sampling as the waiting time of barrier 1 (the SMs finish phase 1 between 24 and 35 us, the same SMs slow
+//     in every step): -3.7 us on phase 2, +2.4 us on phase 1;
+//   * phase 2 as load-compute-store per row: 57.6 us; as a row stream through the ring: 53.8 us; 18 warps per SM,
+//     not 16 or 20 (the batch of 20 000 splits worse over their quarters);
+//   * the kernel sits exactly at its register budget (18 warps = 5 per scheduler = 96 registers): one more live
+//     value in the step loop (a debug stamp) cost 4.5 us per step -- keep the step loop as it is.
 #include <cstdlib>
 #include "mke_rel_persist.cuh"
 
@@ -48,6 +55,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __noinline__ void wait_failed(uint32_t* sync, uint32_t code) {
   atomicExch(sync + kSyncError, code);
@@ -116,18 +125,21 @@ __device__ __forceinline__ uint32_t take_ticket(uint32_t* ctr, int lane) {
   return __shfl_sync(kFull, v, 0);
 }
 
-// one ticket of the apply queue: kApplyChunk flag bytes (large tables) or four rows (tables without flags)
-constexpr int kApplyChunk = 16;
+// one ticket of the apply queue: `chunk` (16 or 32) flag bytes (large tables) or four rows (tables without flags)
 template <int FPL>
-__device__ __forceinline__ void apply_item(const ApplyTable& T, int item, int lane) {
-  if (T.touched != nullptr)
-    apply_flag_chunk<FPL, kApplyChunk>(T, item * kApplyChunk, lane);
-  else
+__device__ __forceinline__ void apply_item(const ApplyTable& T, int item, int chunk, int lane) {
+  if (T.touched != nullptr) {
+    if (chunk == 16)
+      apply_flag_chunk<FPL, 16>(T, item * 16, lane);
+    else
+      apply_flag_chunk<FPL, 32>(T, item * 32, lane);
+  } else {
     apply_row4<FPL>(T, item * 4, lane);
+  }
 }
-__host__ __device__ __forceinline__ int apply_items(const ApplyTable& T) {
+__host__ __device__ __forceinline__ int apply_items(const ApplyTable& T, int chunk) {
   if (T.rows <= 0) return 0;
-  return T.touched != nullptr ? (T.rows + kApplyChunk - 1) / kApplyChunk : (T.rows + 3) / 4;
+  return T.touched != nullptr ? (T.rows + chunk - 1) / chunk : (T.rows + 3) / 4;
 }
 
 // The three phase bodies are separate functions so that each gets its own register allocation (the
@@ -139,17 +151,141 @@ static __device__ __noinline__ float phase1_rows(const RelStepParams& p, const S
   return q8p_stream<FPL, D, false>(p, b, passes, Q, g, ring_w, ids_q, rel_grad, lane);
 }
 
+// Phase 2 as a ROW STREAM (large flagged table): the g, v, acc rows of the next round of four flagged rows
+// travel through the warp's shared-memory ring (2 x 3 slots, cp.async) while the current round is computed,
+// across chunk and ticket boundaries -- twice the bytes in flight of the load-compute-store loop of
+// apply_flag_chunk without holding a register for them.  Chunks of `chunk` flag bytes come by ticket;
+// the ticket after the next and the flag bytes of the next chunk are requested one chunk ahead, so the chain
+// ticket -> flags -> rows never stalls the stream.
+template <int FPL>
+struct ApplyStream {
+  static constexpr int stride = FPL * 8;
+  const ApplyTable& T;
+  uint32_t* ctr;
+  const int item0, n_items;  // tickets item0 .. item0 + n_items - 1 are chunks 0 .. n_items - 1 of T
+  const int chunk;           // flag bytes per chunk: 16 or 32
+  const int lane;
+  uint32_t cur_m = 0;
+  int cur_base = 0;
+  int nx_item;       // chunk whose flag byte this lane already holds (or >= n_items: none)
+  uint8_t nx_flag = 0;
+  __device__ __forceinline__ ApplyStream(const ApplyTable& t, uint32_t* c, int i0, int n, int first_item, int ch, int ln)
+      : T(t), ctr(c), item0(i0), n_items(n), chunk(ch), lane(ln), nx_item(first_item) {
+    load_flag();
+  }
+  __device__ __forceinline__ void load_flag() {
+    const int my = nx_item * chunk + lane;
+    nx_flag = (nx_item < n_items && lane < chunk && my < T.rows) ? T.touched[my] : (uint8_t)0;
+  }
+  // next round of (up to) four flagged rows: this quarter's row offset, or on == false.  Returns false at the end.
+  __device__ __forceinline__ bool next(size_t& off, bool& on) {
+    while (cur_m == 0u) {
+      if (nx_item >= n_items) return false;
+      const bool flag = nx_flag != 0;
+      cur_m = __ballot_sync(kFullMask, flag);
+      cur_base = nx_item * chunk;
+      if (flag) T.touched[cur_base + lane] = 0;
+      const uint32_t t = take_ticket(ctr, lane);
+      nx_item = (int)t - item0;
+      load_flag();
+    }
+    const int q = lane >> 3;
+    uint32_t mm = cur_m;
+    int bit = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = mm ? (__ffs(mm) - 1) : -1;
+      if (k == q) bit = b;
+      mm &= mm - 1;
+    }
+    cur_m = mm;
+    on = bit >= 0;
+    off = (size_t)(cur_base + (on ? bit : 0)) * stride;
+    return true;
+  }
+};
+
 template <int FPL>
 static __device__ __noinline__ void phase2_apply(const PersistParams& q, uint32_t* ctr, const int items_b,
-                                                 const int items_all, const int lane) {
+                                                 const int items_all, unsigned char* ring_w, const int lane) {
+  using Ring = Stage<FPL, 6>;
+  const int sub = lane & 7;
   uint32_t it = take_ticket(ctr, lane);
-  while ((int)it < items_all) {
-    const uint32_t nx = take_ticket(ctr, lane);
-    if ((int)it < items_b)
-      apply_item<FPL>(q.B, (int)it, lane);
-    else
-      apply_item<FPL>(q.A, (int)it - items_b, lane);
-    it = nx;
+  // the small table first (no flags, gradient replicas): one item = four rows, load-compute-store
+  while ((int)it < items_b) {
+    apply_item<FPL>(q.B, (int)it, q.apply_chunk, lane);
+    it = take_ticket(ctr, lane);
+  }
+  if ((int)it >= items_all) return;
+  const ApplyTable& T = q.A;
+  if (T.touched == nullptr || T.replicas > 1 || q.apply_mode == 0) {  // (or not asked for): item by item
+    while ((int)it < items_all) {
+      const uint32_t nx = take_ticket(ctr, lane);
+      apply_item<FPL>(T, (int)it - items_b, q.apply_chunk, lane);
+      it = nx;
+    }
+    return;
+  }
+  Ring stg;
+  stg.base = (uint32_t)__cvta_generic_to_shared(ring_w);
+  stg.lane = lane;
+  ApplyStream<FPL> st(T, ctr, items_b, items_all - items_b, (int)it - items_b, q.apply_chunk, lane);
+  auto issue = [&](int set, size_t off) {
+    stg.issue(3 * set + 0, T.grad + off, sub);
+    stg.issue(3 * set + 1, T.var + off, sub);
+    stg.issue(3 * set + 2, T.acc + off, sub);
+    cp_async_commit();
+  };
+  size_t off_a, off_b = 0;
+  bool on_a, on_b = false;
+  if (!st.next(off_a, on_a)) return;
+  issue(0, off_a);
+  int set = 0;
+  while (true) {
+    const bool more = st.next(off_b, on_b);
+    if (more) {
+      issue(set ^ 1, off_b);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    float g[FPL], v[FPL], a[FPL];
+    stg.read(3 * set + 0, g);
+    stg.read(3 * set + 1, v);
+    stg.read(3 * set + 2, a);
+    float inv = 1.f, coef = 0.f;
+    if (T.normalised) {
+      float ss = 0.f, vg = 0.f;
+#pragma unroll
+      for (int k = 0; k < FPL; ++k) {
+        ss = fmaf(v[k], v[k], ss);
+        vg = fmaf(v[k], g[k], vg);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(kFullMask, ss, o);
+        vg += __shfl_xor_sync(kFullMask, vg, o);
+      }
+      // y = v * rsqrt(max(|v|^2, eps)); the max() routes no gradient to |v|^2 below eps (as apply_one_row)
+      inv = rsqrtf(fmaxf(ss, kNormEps));
+      coef = (ss >= kNormEps) ? vg * inv * inv : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < FPL; ++k) {
+      const float gv = (g[k] - v[k] * coef) * inv;
+      a[k] = fmaf(gv, gv, a[k]);
+      v[k] -= gv * T.lr * (a[k] > 0.f ? rsqrtf(a[k]) : 0.f);  // ApplyAdagrad, no epsilon [TF semantics]
+      g[k] = 0.f;
+    }
+    if (on_a) {
+      q_store<FPL>(T.var + off_a, sub, v);
+      q_store<FPL>(T.acc + off_a, sub, a);
+      q_store<FPL>(T.grad + off_a, sub, g);
+    }
+    if (!more) break;
+    off_a = off_b;
+    on_a = on_b;
+    set ^= 1;
   }
 }
 
@@ -182,10 +318,11 @@ static __device__ __noinline__ void sample_queue(const RelStepParams& p, const P
 template <int FPL, int D, int W, int S>
 __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S))
     rel_step_persist_kernel(const __grid_constant__ RelStepParams p, const __grid_constant__ PersistParams q) {
-  using Ring = Stage<FPL, D>;
+  using Ring = Stage<FPL, (D > 6 ? D : 6)>;  // phase 1 uses D slots of it, phase 2 two sets of three
   extern __shared__ __align__(128) unsigned char s_dyn[];
   unsigned char* const s_ring = s_dyn;                                           // [W][Ring::kBytes]
   int32_t* const s_ids = reinterpret_cast<int32_t*>(s_dyn + W * Ring::kBytes);  // [W + S][4][2][kIdStride]
+  float* const s_loss = reinterpret_cast<float*>(s_ids + (W + S) * kQPerWarp * 2 * kIdStride);  // [W]
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7;
   const int qi = lane >> 3;
@@ -213,7 +350,7 @@ __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S
     block_sync();
     if (threadIdx.x == 0) {
       if (tracer) bt(0) = gtimer_raw();
-      __threadfence();  // release: the block's writes and reductions (ordered before by bar.sync)
+      if (q.fence_mode) fence_acq_rel(); else __threadfence();  // release: the block's writes and reductions (ordered before by bar.sync)
       atomicAdd(q.sync + kSyncBarrier, 1u);
       if (tracer) bt(1) = gtimer_raw();
       const uint32_t target = (round + 1) * gridDim.x;
@@ -222,8 +359,7 @@ __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S
         __nanosleep(100);
         if (gtimer_raw() - t0 > kWaitLimitNs) wait_failed(q.sync, 1u);
       }
-      if (tracer) bt(2) = gtimer_raw();
-      __threadfence();  // acquire + L1 invalidation for the whole SM
+      if (q.fence_mode) fence_acq_rel(); else __threadfence();  // acquire + L1 invalidation for the whole SM (MEMBAR + CCTL.IVALL)
       if (tracer) bt(3) = gtimer_raw();
     }
     block_sync();
@@ -241,9 +377,12 @@ __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S
   if (sampler) {
 #pragma unroll 1
     for (int s = 0; s < q.n_steps; ++s) {
+      // samp_phase 1: sample only under phase 2 (idle in the hardware barrier during phase 1, where extra
+      // warps were measured to cost the row stream 5 us); 0: all through the step
+      if (q.samp_phase == 1) barrier(false);
       if (s + 1 < q.n_steps)
         sample_queue(p, q, s + 1, step_slice_dev(q, s + 1), q.sync + kSyncQueues + 2 * (s + 1) + 1, pick, lane);
-      ++round;  // barrier 1 is the workers'
+      if (q.samp_phase != 1) ++round;  // barrier 1 is the workers'
       barrier(false);
     }
     return;
@@ -251,7 +390,7 @@ __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S
 
   unsigned char* const ring_w = s_ring + wib * Ring::kBytes;
   float* const rel_grad = rel_grad_replica(p);
-  const int items_b = apply_items(q.B), items_all = items_b + apply_items(q.A);
+  const int items_b = apply_items(q.B, q.apply_chunk), items_all = items_b + apply_items(q.A, q.apply_chunk);
 #pragma unroll 1
   for (int s = 0; s < q.n_steps; ++s) {
     const int n = cur.len1 + cur.len2;
@@ -264,15 +403,22 @@ __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S
       const float loss_local = phase1_rows<FPL, D>(p, b, passes, Q, g, ring_w, ids_q, rel_grad, lane);
       float v = (sub == 0) ? loss_local : 0.f;
       v = warp_sum(v);
-      if (lane == 0 && v != 0.f) atomicAdd(q.step_loss + s, (double)v);
+      if (lane == 0) s_loss[wib] = v;
+      asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
+      if (threadIdx.x == 0) {  // one fp64 atomic per block and step
+        double a = 0.0;
+#pragma unroll 1
+        for (int w = 0; w < W; ++w) a += (double)s_loss[w];
+        if (a != 0.0) atomicAdd(q.step_loss + s, a);
+      }
     }
-    barrier(true);
+    barrier(S == 0 || q.samp_phase != 1);
     if (leader && q.host_loss != nullptr && n > 0) {
       const double v = __ldcg(q.step_loss + s);
       *reinterpret_cast<volatile double*>(q.host_loss + s) = v;
     }
     // ---- phase 2, then whatever the sampler warps have left of the next step's negatives --------------
-    if (n > 0) phase2_apply<FPL>(q, q.sync + kSyncQueues + 2 * s, items_b, items_all, lane);
+    if (n > 0) phase2_apply<FPL>(q, q.sync + kSyncQueues + 2 * s, items_b, items_all, ring_w, lane);
     if (has_next) sample_queue(p, q, s + 1, nxt, q.sync + kSyncQueues + 2 * (s + 1) + 1, pick, lane);
     barrier(false);
     cur = nxt;
@@ -282,8 +428,9 @@ __global__ void __launch_bounds__((W + S) * 32, 1) __maxnreg__(ps_max_regs(W + S
 template <int FPL, int D, int W, int S>
 static int launch_persist(const RelStepParams& p, const PersistParams& q, cudaStream_t stream) {
   auto kern = rel_step_persist_kernel<FPL, D, W, S>;
-  using Ring = Stage<FPL, D>;
-  constexpr size_t smem = (size_t)W * Ring::kBytes + (size_t)(W + S) * kQPerWarp * 2 * kIdStride * sizeof(int32_t);
+  using Ring = Stage<FPL, (D > 6 ? D : 6)>;
+  constexpr size_t smem = (size_t)W * Ring::kBytes + (size_t)(W + S) * kQPerWarp * 2 * kIdStride * sizeof(int32_t) +
+                          W * sizeof(float);
   static bool configured = false;
   if (!configured) {
     if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
@@ -307,15 +454,17 @@ static int launch_persist(const RelStepParams& p, const PersistParams& q, cudaSt
   return 0;
 }
 
-// workers + samplers per block: 20 warps at stride <= 80 (5 per scheduler: 96 registers each), 16 above
+// workers + samplers per block: up to 20 warps at stride <= 80 (5 per scheduler: 96 registers each), 16 above.
+// MKE_PERSIST_SPLIT = 10 W' + S picks W = WARPS - W' workers and S samplers (experiments; default below).
 template <int FPL, int D, int WARPS>
 static int launch_persist_split(const RelStepParams& p, const PersistParams& q, cudaStream_t stream) {
-  static const int samplers = getenv("MKE_PERSIST_SAMPLERS") ? atoi(getenv("MKE_PERSIST_SAMPLERS")) : 2;
-  switch (samplers) {
-    case 1: return launch_persist<FPL, D, WARPS - 1, 1>(p, q, stream);
-    case 3: return launch_persist<FPL, D, WARPS - 3, 3>(p, q, stream);
-    case 4: return launch_persist<FPL, D, WARPS - 4, 4>(p, q, stream);
-    default: return launch_persist<FPL, D, WARPS - 2, 2>(p, q, stream);
+  static const int split = getenv("MKE_PERSIST_SPLIT") ? atoi(getenv("MKE_PERSIST_SPLIT")) : 20;
+  switch (split) {
+    case 0: return launch_persist<FPL, D, WARPS, 0>(p, q, stream);
+    case 2: return launch_persist<FPL, D, WARPS - 2, 2>(p, q, stream);
+    case 22: return launch_persist<FPL, D, WARPS - 4, 2>(p, q, stream);
+    case 40: return launch_persist<FPL, D, WARPS - 4, 0>(p, q, stream);
+    default: return launch_persist<FPL, D, WARPS - 2, 0>(p, q, stream);
   }
 }
 

@@ -34,7 +34,11 @@ struct PersistParams {
   double* step_loss;   // device, step s of this launch adds to step_loss[s]
   double* host_loss;   // device-visible pinned host memory or NULL: step_loss[s] is stored there after phase 1
   unsigned long long* trace;  // NULL or [2 * n_steps + 2] globaltimer stamps: start, then after each barrier
-  unsigned long long* block_trace;  // debug (MKE_PERSIST_BLOCKTRACE): [barrier][block][4] stamps of warp 0: arrive, fenced, filler done, released, else NULL
+  int samp_phase;      // sampler warps (experiment, MKE_PERSIST_SPLIT): 1 = sample under phase 2 only, 0 = all through the step
+  int fence_mode;      // barrier fences: 0 = fence.sc (__threadfence), 1 = fence.acq_rel (measured: no difference)
+  int apply_mode;      // 1: phase 2 of the flagged table as a cp.async row stream, 0: load-compute-store per row
+  int apply_chunk;     // flag bytes per apply ticket: 16 or 32
+  unsigned long long* block_trace;  // debug (built with -DMKE_PERSIST_TRACE, MKE_PERSIST_BLOCKTRACE=<file>): [barrier][block][4] stamps of thread 0: arrived, fenced, (barrier 2: own apply share done), released, else NULL
 };
 
 // returns 1 when the launch shape has no instantiation (caller falls back to one launch per phase)

@@ -13,6 +13,7 @@ No TF, no CPU fallback: every call goes through the C-ABI library (multike_b200/
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -40,7 +41,7 @@ class RelationView:
     SLOT = "relation"  # one Adagrad accumulator set per loss graph (MultiKE_model.py:28-31)
 
     def __init__(self, n_ent, n_rel, dim, triples1, triples2, ent_split, batch_size=5000, neg_num=10,
-                 lr=0.001, seed=0, device="cuda", variant=3, ent_init=None, rel_init=None,
+                 lr=0.001, seed=0, device="cuda", variant=4, ent_init=None, rel_init=None,
                  filter1=None, filter2=None, generator=None, pipelined=True, entities1=None, entities2=None,
                  persist_chunk=None):
         self._lib = _cabi.load()
@@ -84,7 +85,7 @@ class RelationView:
         self._persist_ws = self._flag_src = None
         self.persist_chunk = 0
         if self.variant == 4 and self.pipelined:
-            self.persist_chunk = min(int(persist_chunk) if persist_chunk else self.triple_steps, 128)
+            self.persist_chunk = min(int(persist_chunk or os.environ.get('MKE_PERSIST_STEPS', 0)) or 128, 128)
             nbytes = int(self._lib.mke_rel_persist_workspace_bytes(self.n1, self.n2, self.batch_size, self.persist_chunk))
             assert nbytes > 0
             self._persist_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)

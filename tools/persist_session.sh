@@ -21,7 +21,6 @@ PY
 timeout 200 python bench.py --variant 3 --no-cpu-baseline > $OUT/bench_v3.json 2> $OUT/bench_v3.err
 python -c "
 import json; d=json.load(open('$OUT/bench_v3.json')); print('v3 value %.1f e2e %.1f us/step %.1f frac %.3f' % (d['value']/1e6, d['e2e']['value']/1e6, d['ms_per_step']*1e3, d['roofline']['frac']))"
-run s2 MKE_PERSIST_SAMPLERS=2 MKE_PERSIST_BLOCKTRACE=$OUT/blocktrace.bin
-run s3 MKE_PERSIST_SAMPLERS=3
-run s4 MKE_PERSIST_SAMPLERS=4
-ls oracle/_ref/code | head -5; timeout 900 python -m pytest tests/test_gpu_run_scripts.py -q > $OUT/run_scripts.log 2>&1; echo "run scripts rc=$?"; tail -30 $OUT/run_scripts.log
+run sp1 MKE_PERSIST_SAMP_PHASE=1
+run sp0 MKE_PERSIST_SAMP_PHASE=0
+run sp1b MKE_PERSIST_SAMP_PHASE=1
