@@ -121,6 +121,7 @@ __device__ __forceinline__ uint32_t sample_negs_quarter(const KgView& kg, int32_
         // the ballots are the barrier between reading pick[] above and compacting it below
         const uint32_t ba = (__ballot_sync(qmask, keepa) >> qshift) & 0xffu;
         const uint32_t bb = (__ballot_sync(qmask, keepb) >> qshift) & 0xffu;
+        __syncwarp(qmask);  // (racecheck does not count a ballot as ordering the shared-memory reads above)
         if (keepa) pick[n_acc + kept + __popc(ba & below)] = ea;
         if (keepb) pick[n_acc + kept + __popc(ba) + __popc(bb & below)] = eb;
         __syncwarp(qmask);
