@@ -204,35 +204,49 @@ def run_sharded(args, rank, world, local_rank):
         dist.barrier()
         torch.cuda.synchronize()
 
-    step_no = 0
-    for _ in range(warmup):
-        sv.step(step_no % spe)
-        step_no += 1
+    import ctypes
+    lib = _cabi.load()
+    sv.train_steps(0, warmup)
+    step_no = warmup
     clocks = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         clocks.start()
-    sv.phase1_events = []
+    _cabi.check(lib.mke_timing_enable(args.steps))  # CUDA events around this rank's phase-1 launches
+    _cabi.check(lib.mke_timing_stride(max(1, args.p1_every)))
     launches0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    positives = 0
     e0.record()
-    for _ in range(args.steps):
-        positives += sv.step(step_no % spe)
-        step_no += 1
+    positives = sv.train_steps(step_no % spe, args.steps)
     e1.record()
     barrier()
+    step_no += args.steps
     launches = _cabi.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
-    p1_ms = sum(a.elapsed_time(b) for a, b in sv.phase1_events) / max(len(sv.phase1_events), 1)
-    sv.phase1_events = None
-    stats = torch.tensor([ms, p1_ms], dtype=torch.float64, device="cuda")
-    counts = torch.tensor([positives, launches], dtype=torch.float64, device="cuda")
+    tot, cnt = ctypes.c_double(0), ctypes.c_int32(0)
+    _cabi.check(lib.mke_timing_read(ctypes.byref(tot), ctypes.byref(cnt)))
+    p1_ms = tot.value / max(cnt.value, 1)
+    _cabi.check(lib.mke_timing_enable(0))
+    # end-to-end leg: every step each rank copies its positives in from pinned HOST memory and its share of the
+    # step loss back out
+    sv.train_steps(step_no % spe, 3, host_fed=True)
+    step_no += 3
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    e2e_pos = sv.train_steps(step_no % spe, args.steps, host_fed=True)
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    assert float(sv.host_losses[: args.steps].sum()) > 0.0
+    walked = sv.positives_walked(step_no % spe, args.steps)  # positives whose ids this rank copies in per call
+    stats = torch.tensor([ms, p1_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([positives, launches, e2e_pos, walked], dtype=torch.float64, device="cuda")
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    ms, p1_ms = [float(x) for x in stats.cpu()]
-    positives, launches = [float(x) for x in counts.cpu()]
+    ms, p1_ms, e2e_ms = [float(x) for x in stats.cpu()]
+    positives, launches, e2e_pos, walked = [float(x) for x in counts.cpu()]
     if rank == 0:
         peak, peak_kind = measured_peak()
         alg_bytes = positives / world / args.steps * bytes_per_positive(dim, K)
@@ -244,20 +258,22 @@ def run_sharded(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "entities": kgs["n_ent"], "relations": kgs["n_rel"],
                        "triples": int(sv.n1 + sv.n2), "dim": dim, "batch": B, "global_batch": B * world, "neg": K,
-                       "steps_per_epoch": spe, "variant": "q8_ldg_red",
+                       "steps_per_epoch": spe, "variant": VARIANT_NAME[sv.variant],
                        "l2": "no flush: per-rank working set exceeds L2 / rows come over NVLink",
                        "parallelism": "entity table row-sharded over %d GPUs, KG-block placement (each KG on half of "
                                       "the ranks; %s; peer gathers + peer reductions inside phase 1), relation "
-                                      "gradients NCCL all-reduced" % (
+                                      "gradient bucket summed through peer memory, flag barriers, C-side step loop" % (
                                           world, "negatives scored on the rank that owns them, endpoint rows over NVLink"
                                           if sv.owner_negs else "positives trained where their rows live")},
             "clocks": clk,
-            # the multi-GPU driver keeps the triple lists resident; the host-fed path is the N=1 line
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "device-resident triple lists at N > 1 (host-fed e2e is measured at N = 1)"},
+            "e2e": {"value": e2e_pos / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": walked * 12 / args.steps, "d2h_bytes_per_step": 8 * world,
+                    "note": "mke_rel_sharded_train_steps with pinned host triple lists: per step every rank copies the "
+                            "positives it walks H2D (all ranks together: h2d_bytes_per_step) and its 8-byte share of the "
+                            "step loss D2H"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "rel_fused_q8_kernel (phase 1, per rank, rows over NVLink)",
+                         "traffic": None, "kernel": P1_KERNEL[sv.variant] + " (phase 1, per rank, rows over NVLink)",
                          "peak_source": peak_kind, "launch_ms": p1_ms, "bytes_per_positive": bytes_per_positive(dim, K)},
         }
         print(json.dumps(line))

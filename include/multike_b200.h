@@ -303,6 +303,56 @@ typedef struct mke_rel_view {
   const uint32_t* persist_flag_src;
 } mke_rel_view_t;
 
+/*
+ * The relation view on the G GPUs of one box (multike_b200/sharded.py): entity table row-sharded over peer-mapped
+ * memory, relation table replicated.  n_steps GLOBAL steps of `global_batch` positives (each rank trains its part:
+ * sharded.py rank_parts / group_parts), issued without a collective library: xchg[k] is rank k's peer-mapped
+ * exchange buffer of rel->rows * rel->stride floats, sync[k] rank k's peer-mapped array of MKE_MAX_SHARDS
+ * uint32 barrier words (zero-initialised); *barrier_seq (host, starts at 0, the same on every rank) counts the
+ * flag barriers issued so far.  Every rank must make the same sequence of calls.  With `side` != main the
+ * negatives of step s+1 are drawn while step s is exchanged and applied.  step_loss[s] (device) receives this
+ * rank's share of the loss of step s; positives_out the positives this rank answers for.
+ * (sharded.py: ShardedRelationView; tests/multi_gpu_check.py compares with one GPU at batch world * B.)
+ */
+typedef struct mke_rel_sharded_view {
+  const mke_table_t* ent;          /* n_shards = world, peer pointers set                                  */
+  const mke_table_t* rel;          /* this rank's replica                                                  */
+  float*  ent_acc;                 /* Adagrad slot of the local shard                                      */
+  float*  rel_acc;
+  float   lr;
+  const int32_t* triples1;         /* device [n1,3]: the WHOLE lists, on every rank                        */
+  const int32_t* triples2;
+  int32_t n1, n2;
+  const mke_kg_sampler_t* kg1;
+  const mke_kg_sampler_t* kg2;
+  int32_t global_batch;            /* world * per-rank batch                                               */
+  int32_t K;
+  uint64_t seed;
+  int32_t world, rank;
+  int32_t by_kg;                   /* positives trained on the ranks of their own KG (KG-block placement)  */
+  int32_t owner_negs;              /* "negatives where they live" (mke_neg_keep_owned)                     */
+  int32_t dummy_row;               /* a row of this shard (owner_negs)                                     */
+  int32_t variant;                 /* phase-1 schedule                                                     */
+  int32_t*  neg_ent[2];
+  uint32_t* neg_side[2];
+  uint32_t* neg_valid[2];          /* owner_negs only                                                      */
+  double* step_loss;               /* device [>= n_steps]                                                  */
+  float*    xchg[MKE_MAX_SHARDS];
+  uint32_t* sync[MKE_MAX_SHARDS];
+  /* host-fed steps (optional): the lists in pinned HOST memory; every step this rank's part is copied into
+   * staging set (step & 1) ([cap * 3] int32 each, cap = the most positives one rank walks in a step) and its
+   * share of the step loss is copied back to host_step_loss[s] */
+  const int32_t* host_triples1;
+  const int32_t* host_triples2;
+  int32_t* stage1[2];
+  int32_t* stage2[2];
+  double*  host_step_loss;
+} mke_rel_sharded_view_t;
+
+int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* view, int32_t first_step, int32_t n_steps,
+                                uint64_t first_global_step, uint32_t* barrier_seq, int64_t* positives_out,
+                                mke_stream_t main, mke_stream_t side);
+
 /* bytes of mke_rel_view_t.persist_ws for triple lists of n1 / n2 rows (0 on bad arguments) */
 int64_t mke_rel_persist_workspace_bytes(int32_t n1, int32_t n2, int32_t batch_size, int32_t chunk_steps);
 

@@ -73,6 +73,27 @@ class MkeRelView(_c.Structure):
     ]
 
 
+class MkeRelShardedView(_c.Structure):
+    _fields_ = [
+        ("ent", _c.POINTER(MkeTable)), ("rel", _c.POINTER(MkeTable)),
+        ("ent_acc", _c.c_void_p), ("rel_acc", _c.c_void_p),
+        ("lr", _c.c_float),
+        ("triples1", _c.c_void_p), ("triples2", _c.c_void_p),
+        ("n1", _c.c_int32), ("n2", _c.c_int32),
+        ("kg1", _c.POINTER(MkeKgSampler)), ("kg2", _c.POINTER(MkeKgSampler)),
+        ("global_batch", _c.c_int32), ("K", _c.c_int32),
+        ("seed", _c.c_uint64),
+        ("world", _c.c_int32), ("rank", _c.c_int32),
+        ("by_kg", _c.c_int32), ("owner_negs", _c.c_int32), ("dummy_row", _c.c_int32), ("variant", _c.c_int32),
+        ("neg_ent", _c.c_void_p * 2), ("neg_side", _c.c_void_p * 2), ("neg_valid", _c.c_void_p * 2),
+        ("step_loss", _c.c_void_p),
+        ("xchg", _c.c_void_p * MKE_MAX_SHARDS), ("sync", _c.c_void_p * MKE_MAX_SHARDS),
+        ("host_triples1", _c.c_void_p), ("host_triples2", _c.c_void_p),
+        ("stage1", _c.c_void_p * 2), ("stage2", _c.c_void_p * 2),
+        ("host_step_loss", _c.c_void_p),
+    ]
+
+
 _PT = _c.POINTER(MkeTable)
 _PS = _c.POINTER(MkeTripleSet)
 _PK = _c.POINTER(MkeKgSampler)
@@ -92,6 +113,8 @@ SIGNATURES = {
                                         _i32, _vp]),
     "mke_neg_keep_owned": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
+    "mke_rel_sharded_train_steps": (_i32, [_c.POINTER(MkeRelShardedView), _i32, _i32, _u64, _c.POINTER(_c.c_uint32),
+                                           _c.POINTER(_c.c_int64), _vp, _vp]),
     "mke_rel_persist_workspace_bytes": (_c.c_int64, [_i32, _i32, _i32, _i32]),
     "mke_attr_cnn_param_count": (_c.c_int64, [_i32]),
     "mke_attr_cnn_workspace_floats": (_c.c_int64, [_i32, _i32]),

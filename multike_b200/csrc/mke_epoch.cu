@@ -34,6 +34,16 @@ struct PhaseTimer {
   long long seen = 0;
 };
 static PhaseTimer g_timer;
+// used by mke_sharded.cu: an event pair around a launch of the timed kernel, when timing is on
+bool timer_begin(cudaStream_t st) {
+  const bool timed = g_timer.used + 2 <= (int)g_timer.ev.size() && (g_timer.seen++ % g_timer.every) == 0;
+  if (timed) cudaEventRecord(g_timer.ev[g_timer.used], st);
+  return timed;
+}
+void timer_end(cudaStream_t st) {
+  cudaEventRecord(g_timer.ev[g_timer.used + 1], st);
+  g_timer.used += 2;
+}
 
 struct Slice {
   int a1, len1, a2, len2;

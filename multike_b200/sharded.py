@@ -5,9 +5,11 @@
     address space (CUDA IPC, mke_ipc_*), and phase 1 gathers rows / reduces gradient rows straight
     through those peer pointers over NVLink -- the exchange is fused into the kernel, there is no
     all-to-all;
-  * the relation table is small and dense: replicated, its gradient bucket is summed with an NCCL
-    all-reduce between phase 1 and phase 2 (that collective is also the point after which every
-    rank's peer reductions have landed);
+  * the relation table is small and dense: replicated; its gradient bucket (176 KB) is summed between
+    phase 1 and phase 2 by a kernel that reads every rank's copy through its peer mapping, and the points
+    at which ranks wait for each other are flag barriers in peer memory (csrc/mke_sharded.cu) -- the step
+    loop is issued from C without a collective library or a host round trip; torch.distributed only
+    carries the IPC handles at set-up and the epoch's loss sum;
   * a global step of G * batch_size positives is split by position: rank k trains positions
     [k n / G, (k+1) n / G) of the concatenated (kg1 slice ++ kg2 slice) batch and draws its
     negatives at RNG coordinate index_base + i, so G ranks draw what one GPU would draw for the
@@ -282,114 +284,130 @@ class ShardedRelationView:
         self._neg_side = torch.empty(2, cap, dtype=torch.int32, device=self.device)
         self._neg_valid = torch.empty(2, cap, dtype=torch.int32, device=self.device)
         self.ent_split = int(ent_split)
-        # opt-in: the step is issued from Python, and the extra events / stream switches cost more host time
-        # than the 15-20 us of sampling they hide (4 x B200: 430 vs 539 M positives/s)
-        self.draw_ahead = os.environ.get("MKE_DRAW_AHEAD", "0") == "1"
+        # the next step's negatives are drawn on a second stream under the exchange and phase 2 (C-side events)
+        self.draw_ahead = os.environ.get("MKE_DRAW_AHEAD", "1") == "1"
         self._side = torch.cuda.Stream(device=self.device)
-        self._events = [(torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
-        self._plans = {}
-        self._ahead = None        # ((step_in_epoch, global_step, list version), buffer set, ready event)
-        self._list_version = 0    # bump when the triple lists are permuted (a prefetch would be stale)
         self.loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self._fence = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._step_loss = torch.zeros(max(self.triple_steps, 1), dtype=torch.float64, device=self.device)
         self.global_step = 0
-        self.phase1_events = None
+        # peer-mapped exchange buffer of the relation gradient bucket and barrier words (csrc/mke_sharded.cu)
+        self._xchg = PeerBuffer((self.rel.rows, self.rel.stride), torch.float32, group)
+        self._sync = PeerBuffer((8,), torch.int32, group)
+        self._barrier_seq = ctypes.c_uint32(0)
+        self._host = self._host_loss = None
+        v = self._view = _cabi.MkeRelShardedView()
+        v.ent, v.rel = ctypes.pointer(self.ent._c), ctypes.pointer(self.rel._c)
+        v.ent_acc = self.ent.adagrad_slot(self.SLOT).data_ptr()
+        v.rel_acc = self.rel.adagrad_slot(self.SLOT).data_ptr()
+        v.lr = self.lr
+        v.triples1, v.triples2, v.n1, v.n2 = self.triples1.data_ptr(), self.triples2.data_ptr(), self.n1, self.n2
+        v.kg1, v.kg2 = ctypes.pointer(self.kg1._c), ctypes.pointer(self.kg2._c)
+        v.global_batch, v.K, v.seed = self.global_batch, self.K, self.seed & (2 ** 64 - 1)
+        v.world, v.rank, v.by_kg, v.owner_negs = self.world, self.rank, int(self.by_kg), int(self.owner_negs)
+        v.dummy_row = self._dummy_row if self.owner_negs else 0
+        v.variant = self.variant
+        for k in range(2):
+            v.neg_ent[k], v.neg_side[k] = self._neg_ent[k].data_ptr(), self._neg_side[k].data_ptr()
+            v.neg_valid[k] = self._neg_valid[k].data_ptr()
+        for k in range(self.world):
+            v.xchg[k], v.sync[k] = self._xchg.peers[k], self._sync.peers[k]
+        torch.cuda.synchronize()
+        dist.barrier(group)
 
     @property
     def triple_steps(self):
         return int(math.ceil((self.n1 + self.n2) / self.global_batch))
 
-    def _plan(self, step_in_epoch):
-        """launch arguments of one global step for this rank: (p1, l1, p2, l2, index_base, own_lo,
-        own_hi, positives this rank answers for); a pure function of the step (lists are permuted in
-        place), so it is computed once per step of an epoch"""
-        plan = self._plans.get(step_in_epoch)
-        if plan is None:
-            plan = self._plans[step_in_epoch] = self._make_plan(step_in_epoch)
-        return plan
-
-    def _make_plan(self, step_in_epoch):
+    def plan(self, step_in_epoch):
+        """(positives of kg1, of kg2, index_base, own_lo, own_hi, positives this rank answers for) of one global
+        step for this rank -- what csrc/mke_sharded.cu::make_plan computes; kept for the CPU tests"""
         if self.owner_negs:
             kg_no, (a, ln), (lo, hi), base = group_parts(self.n1, self.n2, self.global_batch, step_in_epoch,
                                                          self.rank, self.world)
-            if kg_no == 1:
-                return self.triples1.data_ptr() + 12 * a, ln, None, 0, base, lo, hi, hi - lo
-            return None, 0, self.triples2.data_ptr() + 12 * a, ln, base, lo, hi, hi - lo
+            return ((a, ln), (0, 0), base, lo, hi, hi - lo) if kg_no == 1 else ((0, 0), (a, ln), base, lo, hi, hi - lo)
         (a1, l1), (a2, l2), base = rank_parts(self.n1, self.n2, self.global_batch, step_in_epoch, self.rank, self.world,
                                                by_kg=self.by_kg)
-        return (self.triples1.data_ptr() + 12 * a1, l1, self.triples2.data_ptr() + 12 * a2, l2, base, 0, 0x7fffffff,
-                l1 + l2)
+        return (a1, l1), (a2, l2), base, 0, 0x7fffffff, l1 + l2
 
-    def _draw(self, plan, global_step, buf, stream):
-        """negatives of a step into buffer set `buf` on `stream` (sampler, then the ownership
-        filter under "negatives where they live")"""
-        p1, l1, p2, l2, base = plan[:5]
-        if self.K == 0 or l1 + l2 == 0:
-            return
-        ne, ns, nv = self._neg_ent[buf], self._neg_side[buf], self._neg_valid[buf]
-        _cabi.check(self._lib.mke_sample_structured_at(
-            p1, l1, self.kg1.c, p2, l2, self.kg2.c, self.K, self.seed & (2 ** 64 - 1), global_step, base,
-            ne.data_ptr(), ns.data_ptr(), stream))
-        if self.owner_negs:
-            _cabi.check(self._lib.mke_neg_keep_owned(ne.data_ptr(), l1 + l2, self.K, self.world, self.ent_split,
-                                                     self.rank, self._dummy_row, nv.data_ptr(), stream))
+    def train_steps(self, first_step, n_steps, host_fed=False):
+        """n_steps consecutive GLOBAL steps starting at step `first_step` of the epoch (wrapping), issued by ONE
+        library call on every rank; returns the number of positives this rank answers for.  The per-step
+        losses of this rank are added to loss_acc.  host_fed: every step this rank's positives are copied in
+        from pinned HOST memory and its share of the step loss is copied back (host_losses)."""
+        if n_steps <= 0:
+            return 0
+        if self._step_loss.numel() < n_steps:
+            self._step_loss = torch.zeros(n_steps, dtype=torch.float64, device=self.device)
+        self._step_loss[:n_steps].zero_()
+        v = self._view
+        v.step_loss = self._step_loss.data_ptr()
+        if host_fed:
+            if self._host is None:
+                cap = self._neg_side.shape[1]
+                self._host = (self.triples1.cpu().pin_memory(), self.triples2.cpu().pin_memory(),
+                              [torch.empty(cap * 3, dtype=torch.int32, device=self.device) for _ in range(4)])
+            if self._host_loss is None or self._host_loss.numel() < n_steps:
+                self._host_loss = torch.zeros(n_steps, dtype=torch.float64).pin_memory()
+            v.host_triples1, v.host_triples2 = self._host[0].data_ptr(), self._host[1].data_ptr()
+            for k in range(2):
+                v.stage1[k], v.stage2[k] = self._host[2][k].data_ptr(), self._host[2][2 + k].data_ptr()
+            v.host_step_loss = self._host_loss.data_ptr()
+        else:
+            v.host_triples1 = v.host_triples2 = v.host_step_loss = None
+        main = torch.cuda.current_stream()
+        mine = ctypes.c_int64(0)
+        side = self._side.cuda_stream if self.draw_ahead else None
+        _cabi.check(self._lib.mke_rel_sharded_train_steps(
+            ctypes.byref(self._view), int(first_step), int(n_steps), self.global_step, ctypes.byref(self._barrier_seq),
+            ctypes.byref(mine), main.cuda_stream, side))
+        self.loss_acc += self._step_loss[:n_steps].sum()
+        self.global_step += n_steps
+        return int(mine.value)
+
+    def positives_walked(self, first_step, n_steps):
+        """positives whose ids this rank reads in steps first_step .. (what a host-fed call copies in)"""
+        tot = 0
+        for k in range(n_steps):
+            (a1, l1), (a2, l2) = self.plan((first_step + k) % self.triple_steps)[:2]
+            tot += l1 + l2
+        return tot
+
+    @property
+    def host_losses(self):
+        return self._host_loss
 
     def step(self, step_in_epoch):
-        """one global step; returns the number of positives this rank answers for.  The negatives of
-        the NEXT step are drawn on a side stream while this step's collectives and phase 2 run."""
-        import torch.distributed as dist
-        main = torch.cuda.current_stream()
-        plan = self._plan(step_in_epoch)
-        p1, l1, p2, l2, base, lo, hi, mine = plan
-        key = (step_in_epoch, self.global_step, self._list_version)
-        if self._ahead is not None and self._ahead[0] == key:
-            buf = self._ahead[1]
-            main.wait_event(self._ahead[2])
-        else:
-            buf = 0 if self._ahead is None else 1 - self._ahead[1]
-            self._draw(plan, self.global_step, buf, main.cuda_stream)
-        self._ahead = None
-        if l1 + l2 > 0:
-            ev = None
-            if self.phase1_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            _cabi.check(self._lib.mke_rel_step_structured3(
-                self.ent.c, self.rel.c, p1, l1, p2, l2, self.K, self._neg_ent[buf].data_ptr(),
-                self._neg_side[buf].data_ptr(), self._neg_valid[buf].data_ptr() if self.owner_negs else None, lo, hi,
-                None, 1.0, self.loss_acc.data_ptr(), self.variant, main.cuda_stream))
-            if ev is not None:
-                ev[1].record()
-                self.phase1_events.append(ev)
-        if self.K > 0 and self.draw_ahead:
-            # the other buffer set was last read by the previous phase 1, which precedes this event
-            nxt = (step_in_epoch + 1) % self.triple_steps
-            done, ready = self._events[buf]
-            done.record(main)
-            self._side.wait_event(done)
-            self._draw(self._plan(nxt), self.global_step + 1, 1 - buf, self._side.cuda_stream)
-            ready.record(self._side)
-            self._ahead = ((nxt, self.global_step + 1, self._list_version), 1 - buf, ready)
-        # dense gradient bucket of the replicated relation table; after it, every rank's phase 1
-        # (and with it every peer reduction into this rank's shard) has completed
-        dist.all_reduce(self.rel.grad, group=self.group)
-        T.apply_adagrad_pair(self.ent, self.ent.adagrad_slot(self.SLOT), self.lr,
-                             self.rel, self.rel.adagrad_slot(self.SLOT), self.lr)
-        # no rank may start the next phase 1 (peer reads of var, peer reductions into grad) before
-        # every rank has finished this phase 2: a stream-ordered one-element all-reduce (no host sync)
-        dist.all_reduce(self._fence, group=self.group)
-        self.global_step += 1
-        return mine
+        """one global step; returns the number of positives this rank answers for"""
+        return self.train_steps(step_in_epoch, 1)
 
-    def train_epoch(self):
+    def shuffle(self, seed):
+        """MultiKE_model.py:314-315 random.shuffle of both triple lists: the SAME permutation on every rank
+        (every rank holds the whole lists), drawn on the host from `seed`"""
+        gen = torch.Generator().manual_seed(int(seed))
+        p1 = torch.randperm(self.n1, generator=gen).to(self.device)
+        p2 = torch.randperm(self.n2, generator=gen).to(self.device)
+        self.triples1.copy_(self.triples1[p1])
+        self.triples2.copy_(self.triples2[p2])
+        if self._host is not None:
+            self._host[0].copy_(self.triples1)
+            self._host[1].copy_(self.triples2)
+
+    def train_epoch(self, shuffle_seed=None):
+        """train_relation_view_1epo on G GPUs: (average loss per positive, positives) over all ranks; the lists
+        are shuffled afterwards when a seed is given (the same one on every rank)"""
         import torch.distributed as dist
         self.loss_acc.zero_()
-        trained = 0
-        for s in range(self.triple_steps):
-            trained += self.step(s)
-        tot = torch.cat([self.loss_acc, torch.tensor([float(trained)], dtype=torch.float64, device=self.device)])
+        trained = self.train_steps(0, self.triple_steps)
+        tot = torch.cat([self.loss_acc, torch.tensor([float(trained)], dtype=torch.float64, device=self.device)]).cpu()
+        if dist.get_backend(self.group) != "gloo":
+            tot = tot.to(self.device)
         dist.all_reduce(tot, group=self.group)
+        if shuffle_seed is not None:
+            self.shuffle(shuffle_seed)
         return float(tot[0]) / max(float(tot[1]), 1.0), int(tot[1])
 
     def close(self):
+        torch.cuda.synchronize()
+        self._xchg.close()
+        self._sync.close()
         self.ent.close()

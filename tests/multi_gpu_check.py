@@ -2,6 +2,9 @@
 a single-GPU run with batch_size G * B (same negatives through index_base) up to fp32 summation
 order.  Prints MULTI_GPU_CHECK PASS on rank 0.  Used by tests/test_gpu_multi.py and by hand:
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+MKE_SAME_GPU=1: all ranks share cuda:0 (a box with ONE GPU): the shards are still separate allocations reached
+through CUDA IPC mappings and the flag barriers still cross process boundaries (the two contexts time-slice the
+GPU, so it is slow); torch.distributed then runs on gloo, which the data path does not use anyway.
 """
 import os
 import sys
@@ -16,8 +19,13 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    same_gpu = os.environ.get("MKE_SAME_GPU", "0") == "1"
+    torch.cuda.set_device(0 if same_gpu else int(os.environ.get("LOCAL_RANK", rank)))
+    if same_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    dev = "cpu" if same_gpu else "cuda"
     from multike_b200 import synthetic, tables as T
     from multike_b200.relation_view import RelationView
     from multike_b200.sharded import ShardedRelationView
@@ -34,9 +42,11 @@ def main():
                              rel_init=rel0, by_kg=by_kg)
     steps = 5
     sv.loss_acc.zero_()
-    trained = sum(sv.step(s) for s in range(steps))
+    # steps 0-2 in one library call, step 3 on its own, step 4 host fed (positives H2D, loss share D2H)
+    trained = sv.train_steps(0, 3) + sv.step(3) + sv.train_steps(4, 1, host_fed=True)
     torch.cuda.synchronize()
-    tot = torch.cat([sv.loss_acc, torch.tensor([float(trained)], dtype=torch.float64, device="cuda")])
+    host_loss_ok = abs(float(sv.host_losses[0]) - float(sv._step_loss[0])) <= 1e-12 * abs(float(sv._step_loss[0]))
+    tot = torch.cat([sv.loss_acc, torch.tensor([float(trained)], dtype=torch.float64, device="cuda")]).to(dev)
     dist.all_reduce(tot)
     # reference: ONE GPU, batch G*B, same seed (every rank computes it for its own comparison)
     rv = RelationView(kgs["n_ent"], kgs["n_rel"], dim, kgs["triples1"], kgs["triples2"], kgs["ent_split"],
@@ -55,12 +65,14 @@ def main():
     ok &= int(tot[1]) == ref_trained
     ok &= abs(float(tot[0]) - ref_loss) <= 1e-5 * abs(ref_loss)
     ok &= float(sv.ent.grad.abs().max()) == 0.0 and (sv.ent.touched is None or int(sv.ent.touched.max()) == 0)
-    flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    ok &= host_loss_ok
+    flags = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     print("rank %d: d_ent %.2e d_rel %.2e d_export %.2e moved %.2e loss %.6f vs %.6f trained %d vs %d" % (
         rank, d_ent, d_rel, d_exp, moved, float(tot[0]), ref_loss, int(tot[1]), ref_trained), flush=True)
     if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if float(flags) == 1.0 else "FAIL", "world", world, "by_kg", by_kg, flush=True)
+        print("MULTI_GPU_CHECK", "PASS" if float(flags) == 1.0 else "FAIL", "world", world, "by_kg", by_kg,
+              "owner_negs", sv.owner_negs, "same_gpu", same_gpu, flush=True)
     sv.close()
     dist.destroy_process_group()
     return 0 if float(flags) == 1.0 else 1

@@ -1,4 +1,6 @@
-"""Multi-GPU relation view on real GPUs (needs >= 2 devices on the box; skipped otherwise)."""
+"""Multi-GPU relation view on real GPUs.  With fewer devices than ranks the world-2 / world-4 cases still run:
+all ranks then share cuda:0 (tests/multi_gpu_check.py, MKE_SAME_GPU) -- separate shard allocations behind CUDA IPC
+mappings, flag barriers across processes -- so the sharded path has parity evidence on a one-GPU box too."""
 import os
 import subprocess
 import sys
@@ -13,10 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("by_kg", ["1", "0"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_relation_view_equals_single_gpu(world, by_kg):
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+    same_gpu = torch.cuda.device_count() < world
+    if same_gpu and world > 4:
+        pytest.skip("needs %d GPUs (the shared-GPU mode is run at world 2 and 4 only: the ranks time-slice one device)" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29510 + world), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    out = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
-                         env=dict(os.environ, MKE_BY_KG=by_kg))
+    out = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                         env=dict(os.environ, MKE_BY_KG=by_kg, MKE_SAME_GPU="1" if same_gpu else "0"))
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-4000:]
