@@ -307,8 +307,8 @@ typedef struct mke_rel_view {
  * The relation view on the G GPUs of one box (multike_b200/sharded.py): entity table row-sharded over peer-mapped
  * memory, relation table replicated.  n_steps GLOBAL steps of `global_batch` positives (each rank trains its part:
  * sharded.py rank_parts / group_parts), issued without a collective library: xchg[k] is rank k's peer-mapped
- * exchange buffer of rel->rows * rel->stride floats, sync[k] rank k's peer-mapped array of MKE_MAX_SHARDS
- * uint32 barrier words (zero-initialised); *barrier_seq (host, starts at 0, the same on every rank) counts the
+ * exchange buffer of 2 * rel->rows * rel->stride floats (two step parities), sync[k] rank k's peer-mapped array of
+ * 2 * MKE_MAX_SHARDS uint32 words (zero-initialised: barrier flags, then two words of this rank's own); *barrier_seq (host, starts at 0, the same on every rank) counts the
  * flag barriers issued so far.  Every rank must make the same sequence of calls.  With `side` != main the
  * negatives of step s+1 are drawn while step s is exchanged and applied.  step_loss[s] (device) receives this
  * rank's share of the loss of step s; positives_out the positives this rank answers for.

@@ -6,13 +6,16 @@
 //
 //   K1 sampler [+ ownership filter]          (side stream, one step ahead, when a side stream is given)
 //   K2 phase 1                                gathers rows / reduces gradient rows through peer pointers
-//   K3 rel_exchange_kernel                    a. my replicas -> my exchange buffer
-//                                             b. barrier A: every rank has finished K2 (its peer reductions into my
-//                                                shard have landed: a kernel's writes are complete when it ends) and
-//                                                filled its exchange buffer
+//   K3 rel_exchange_kernel (cooperative,      a. my replicas -> my exchange buffer of this step's parity
+//      32 blocks)                             b. barrier A (the last block to finish a. does it, the others wait on a
+//                                                local flag): every rank has finished K2 (its peer reductions into
+//                                                my shard have landed: a kernel's writes are complete when it ends)
+//                                                and filled its exchange buffer
 //                                             c. sum of all exchange buffers, in rank order (identical bits on
 //                                                every rank) -> my gradient replica 0
-//                                             d. barrier B: every rank has read every buffer
+//                                             (the buffers are double-buffered by step parity: a buffer is rewritten
+//                                             two steps later, after barrier A of the step in between, at which
+//                                             every rank has long finished reading it -- no barrier after c.)
 //   K4 phase 2                                local shard + relation replica (MultiKE_model.py:15-31)
 //   K5 peer_barrier_kernel                    barrier C: nobody starts the next phase 1 (peer reads of var, peer
 //                                             reductions into grad) before everybody's phase 2 has ended
@@ -57,17 +60,23 @@ __device__ __forceinline__ void peer_barrier(const PeerSync& ps, uint32_t seq) {
 
 struct ExchangeParams {
   PeerSync ps;
-  float* xchg[MKE_MAX_SHARDS];  // every rank's exchange buffer [n4 float4]
+  float* xchg[MKE_MAX_SHARDS];  // every rank's exchange buffers: 2 (step parity) x n4 float4
   float* grad;                  // my relation gradient: `replicas` copies of n4 float4 each
+  uint32_t* local;              // my words [0]: block arrivals (monotonic), [1]: released-up-to sequence number
   int replicas;
   int n4;
-  uint32_t seq;                 // barriers seq (A) and seq + 1 (B)
+  uint32_t seq;                 // sequence number of barrier A
+  uint32_t launch_no;           // exchange launches before this one
 };
 
-__global__ void __launch_bounds__(1024) rel_exchange_kernel(const ExchangeParams p) {
-  float4* const mine = reinterpret_cast<float4*>(p.xchg[p.ps.rank]);
+constexpr int kXBlocks = 32, kXThreads = 256;
+
+__global__ void __launch_bounds__(kXThreads) rel_exchange_kernel(const ExchangeParams p) {
+  const size_t half = (size_t)(p.launch_no & 1u) * p.n4;
+  float4* const mine = reinterpret_cast<float4*>(p.xchg[p.ps.rank]) + half;
   float4* const g = reinterpret_cast<float4*>(p.grad);
-  for (int i = threadIdx.x; i < p.n4; i += blockDim.x) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < p.n4; i += nth) {
     float4 s = g[i];
     for (int r = 1; r < p.replicas; ++r) {
       s = f4_add(s, g[(size_t)r * p.n4 + i]);
@@ -75,14 +84,38 @@ __global__ void __launch_bounds__(1024) rel_exchange_kernel(const ExchangeParams
     }
     mine[i] = s;
   }
-  peer_barrier(p.ps, p.seq);
-  for (int i = threadIdx.x; i < p.n4; i += blockDim.x) {
+  // grid-wide: the last block to get here talks to the peers, the others wait for its word
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t old = atomicAdd(p.local, 1u);
+    s_last = (old + 1u == (p.launch_no + 1u) * gridDim.x) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    peer_barrier(p.ps, p.seq);
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.local + 1), "r"(p.seq) : "memory");
+  } else if (threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)::"memory");
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.local + 1) : "memory");
+      if ((int32_t)(v - p.seq) >= 0) break;
+      __nanosleep(100);
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)::"memory");
+      if (t1 - t0 > kPeerWaitNs) __trap();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < p.n4; i += nth) {
     float4 s = f4_zero();
     for (int k = 0; k < p.ps.world; ++k)  // rank order: the same sum on every rank
-      s = f4_add(s, __ldcg(reinterpret_cast<const float4*>(p.xchg[k]) + i));
+      s = f4_add(s, __ldcg(reinterpret_cast<const float4*>(p.xchg[k]) + half + i));
     g[i] = s;
   }
-  peer_barrier(p.ps, p.seq + 1u);
 }
 
 __global__ void peer_barrier_kernel(const PeerSync ps, uint32_t seq) { peer_barrier(ps, seq); }
@@ -186,6 +219,7 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
     x.ps.flags[k] = v->sync[k];
     x.xchg[k] = v->xchg[k];
   }
+  x.local = v->sync[v->rank] + MKE_MAX_SHARDS;
   x.grad = v->rel->grad;
   x.replicas = v->rel->grad_replicas > 1 ? v->rel->grad_replicas : 1;
   x.n4 = v->rel->rows * v->rel->stride / 4;
@@ -260,14 +294,18 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
       if (rc) break;
       if (ahead) cudaEventRecord(ev_ready, side);
     }
-    x.seq = *barrier_seq + 1u;
-    *barrier_seq += 3u;
-    rel_exchange_kernel<<<1, 1024, 0, main>>>(x);
-    count_launch();
-    if (cudaError_t e = cudaGetLastError()) { rc = cuda_fail(e, "rel_exchange_kernel"); break; }
+    x.seq = *barrier_seq + 1u;     // barrier A; barrier C is seq + 1
+    x.launch_no = *barrier_seq / 2u;
+    *barrier_seq += 2u;
+    {
+      void* args[] = {(void*)&x};
+      cudaError_t e = cudaLaunchCooperativeKernel((const void*)rel_exchange_kernel, dim3(kXBlocks), dim3(kXThreads), args, 0, main);
+      count_launch();
+      if (e != cudaSuccess) { rc = cuda_fail(e, "rel_exchange_kernel"); break; }
+    }
     rc = mke_rows_apply_adagrad_pair(v->ent, v->ent_acc, v->lr, v->rel, v->rel_acc, v->lr, main);
     if (rc) break;
-    peer_barrier_kernel<<<1, 32, 0, main>>>(x.ps, x.seq + 2u);
+    peer_barrier_kernel<<<1, 32, 0, main>>>(x.ps, x.seq + 1u);
     count_launch();
     if (cudaError_t e = cudaGetLastError()) { rc = cuda_fail(e, "peer_barrier_kernel"); break; }
     if (have_next && ahead) cudaStreamWaitEvent(main, ev_ready, 0);

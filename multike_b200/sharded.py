@@ -291,8 +291,8 @@ class ShardedRelationView:
         self._step_loss = torch.zeros(max(self.triple_steps, 1), dtype=torch.float64, device=self.device)
         self.global_step = 0
         # peer-mapped exchange buffer of the relation gradient bucket and barrier words (csrc/mke_sharded.cu)
-        self._xchg = PeerBuffer((self.rel.rows, self.rel.stride), torch.float32, group)
-        self._sync = PeerBuffer((8,), torch.int32, group)
+        self._xchg = PeerBuffer((2, self.rel.rows, self.rel.stride), torch.float32, group)
+        self._sync = PeerBuffer((16,), torch.int32, group)
         self._barrier_seq = ctypes.c_uint32(0)
         self._host = self._host_loss = None
         v = self._view = _cabi.MkeRelShardedView()

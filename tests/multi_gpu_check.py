@@ -68,11 +68,15 @@ def main():
     ok &= host_loss_ok
     flags = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    print("rank %d: d_ent %.2e d_rel %.2e d_export %.2e moved %.2e loss %.6f vs %.6f trained %d vs %d" % (
-        rank, d_ent, d_rel, d_exp, moved, float(tot[0]), ref_loss, int(tot[1]), ref_trained), flush=True)
+    # one write per line: the ranks share a pipe
+    sys.stdout.write("rank %d: d_ent %.2e d_rel %.2e d_export %.2e moved %.2e loss %.6f vs %.6f trained %d vs %d\n" % (
+        rank, d_ent, d_rel, d_exp, moved, float(tot[0]), ref_loss, int(tot[1]), ref_trained))
+    sys.stdout.flush()
+    dist.barrier()
     if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if float(flags) == 1.0 else "FAIL", "world", world, "by_kg", by_kg,
-              "owner_negs", sv.owner_negs, "same_gpu", same_gpu, flush=True)
+        sys.stdout.write("MULTI_GPU_CHECK %s world %d by_kg %s owner_negs %s same_gpu %s\n" % (
+            "PASS" if float(flags) == 1.0 else "FAIL", world, by_kg, sv.owner_negs, same_gpu))
+        sys.stdout.flush()
     sv.close()
     dist.destroy_process_group()
     return 0 if float(flags) == 1.0 else 1
