@@ -456,6 +456,19 @@ int mke_rel_step_structured3(const mke_table_t* ent, const mke_table_t* rel,
 /* ------------------------------------------------------------------------------------------
  * Peer memory for row-sharded tables (one process per GPU; handles travel over torch.distributed).
  * ------------------------------------------------------------------------------------------ */
+/* mke_neg_keep_owned, COMPACTED: this rank's negatives first (original order), dummies behind, the side word
+ * permuted along; neg_valid[i] = low_ones(count).  With compact = 1 mke_rel_step_structured4 (otherwise
+ * mke_rel_step_structured3) lets the one-wave kernel (variant 0) stop its K-loop at the longest list of a warp's
+ * four positives. */
+int mke_neg_keep_owned2(int32_t* neg_ent, uint32_t* neg_side, int32_t n, int32_t K, int32_t n_shards,
+                        int32_t shard_split, int32_t my_shard, int32_t dummy_id, uint32_t* neg_valid,
+                        mke_stream_t stream);
+int mke_rel_step_structured4(const mke_table_t* ent, const mke_table_t* rel, const int32_t* pos1, int32_t len1,
+                             const int32_t* pos2, int32_t len2, int32_t K, const int32_t* neg_ent,
+                             const uint32_t* neg_side, const uint32_t* neg_valid_or_null, int32_t compact,
+                             int32_t pos_own_lo, int32_t pos_own_hi, const float* w_or_null, float pos_scale,
+                             double* loss_accum, int32_t variant, mke_stream_t stream);
+
 int mke_peer_alloc(uint64_t bytes, void** ptr);                  /* cudaMalloc + zero fill          */
 int mke_peer_free(void* ptr);
 int mke_ipc_export(const void* ptr, unsigned char handle[64]);   /* cudaIpcGetMemHandle             */

@@ -112,6 +112,9 @@ SIGNATURES = {
     "mke_rel_step_structured3": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp,
                                         _i32, _vp]),
     "mke_neg_keep_owned": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mke_neg_keep_owned2": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mke_rel_step_structured4": (_i32, [_PT, _PT, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _f32,
+                                        _vp, _i32, _vp]),
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
     "mke_rel_sharded_train_steps": (_i32, [_c.POINTER(MkeRelShardedView), _i32, _i32, _u64, _c.POINTER(_c.c_uint32),
                                            _c.POINTER(_c.c_int64), _vp, _vp]),

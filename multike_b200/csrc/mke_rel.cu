@@ -645,6 +645,17 @@ extern "C" int mke_rel_step_structured3(const mke_table_t* ent, const mke_table_
                                         int32_t pos_own_lo, int32_t pos_own_hi, const float* w_or_null,
                                         float pos_scale, double* loss_accum, int32_t variant,
                                         mke_stream_t stream) {
+  return mke_rel_step_structured4(ent, rel, pos1, len1, pos2, len2, K, neg_ent, neg_side, neg_valid_or_null, 0,
+                                  pos_own_lo, pos_own_hi, w_or_null, pos_scale, loss_accum, variant, stream);
+}
+
+extern "C" int mke_rel_step_structured4(const mke_table_t* ent, const mke_table_t* rel,
+                                        const int32_t* pos1, int32_t len1, const int32_t* pos2,
+                                        int32_t len2, int32_t K, const int32_t* neg_ent,
+                                        const uint32_t* neg_side, const uint32_t* neg_valid_or_null,
+                                        int32_t compact, int32_t pos_own_lo, int32_t pos_own_hi,
+                                        const float* w_or_null, float pos_scale, double* loss_accum,
+                                        int32_t variant, mke_stream_t stream) {
   if (int rc = validate_tables(ent, rel)) return rc;
   MKE_CHECK_ARG(pos_own_lo >= 0 && pos_own_hi >= pos_own_lo, "bad owner range [%d, %d)", pos_own_lo, pos_own_hi);
   MKE_CHECK_ARG(K >= 0 && K <= MKE_MAX_NEG, "K=%d outside [0,%d]", K, MKE_MAX_NEG);
@@ -666,6 +677,7 @@ extern "C" int mke_rel_step_structured3(const mke_table_t* ent, const mke_table_
   p.neg_ent = neg_ent;
   p.neg_side = neg_side;
   p.neg_valid = neg_valid_or_null;
+  p.neg_compact = (compact != 0 && neg_valid_or_null != nullptr) ? 1 : 0;
   p.pos_own_lo = pos_own_lo;
   p.pos_own_hi = pos_own_hi;
   p.w = w_or_null;

@@ -40,6 +40,7 @@ struct RelStepParams {
   // contributes nothing); the positive term of positive i is this launch's only if
   // pos_own_lo <= i < pos_own_hi.  NULL / [0, INT_MAX) => everything is this launch's.
   const uint32_t* neg_valid;
+  int neg_compact;  // neg_valid words are low_ones(count): this launch's negatives come first (mke_neg_keep_owned2)
   int pos_own_lo, pos_own_hi;
   const float* w;
   float pos_scale;

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
     {
       uint32_t side = 0u;
       uint32_t mine = 0xffffffffu;  // negatives of this positive that are this launch's (RelStepParams.neg_valid)
+      int Kw = K;                   // rows the K-loop of this warp walks
       const bool active = valid;
       const bool pos_on = valid && i >= p.pos_own_lo && i < p.pos_own_hi;
       if (h + r + t == -3) MKE_TRACE(15);  // (forces the id loads to have landed)
@@ -101,6 +102,14 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
           if (p.neg_valid != nullptr && valid) mine = __ldg(p.neg_valid + i);
         }
         __syncwarp();
+        // "negatives where they live", compacted (mke_neg_keep_owned2: this launch's negatives first): the
+        // K-loop only runs as far as the longest list of the warp's four positives
+        if (p.neg_compact) {
+          int cnt = valid ? __popc(mine & low_ones(K)) : 0;
+          cnt = max(cnt, __shfl_xor_sync(kFull, cnt, 8));
+          cnt = max(cnt, __shfl_xor_sync(kFull, cnt, 16));
+          Kw = cnt;
+        }
         if (p.neg_out != nullptr && active) {
           for (int c = sub; c < K; c += 8) {
             const bool hs = (side >> c) & 1u;
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
         // the slots are free again (their contents fed the sums above): first negatives go out
 #pragma unroll
         for (int j = 0; j < kSlots; ++j) {
-          if (j < K) stg.issue(j, ent_var_row(p, pick[j], stride), sub);
+          if (j < Kw) stg.issue(j, ent_var_row(p, pick[j], stride), sub);
           cp_async_commit();
         }
         const float ih = p.ent_norm ? rsqrtf(fmaxf(sh, kNormEps)) : 1.f;
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
       MKE_TRACE(4);
       // ---- negatives: rows j+1, j+2 are in flight while row j is scored ------------------------
       int slot = 0;
-      for (int j = 0; j < K; ++j) {
+      for (int j = 0; j < Kw; ++j) {
         if (j < 8) MKE_TRACE(5 + j);
         float x[FPL];
         cp_async_wait<kSlots - 1>();
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rel_fused_q8_kernel(const RelSt
           be = fmaf(x[k], base[k], be);
         }
         // slot is free: request row j + kSlots (the sums above consumed x)
-        if (j + kSlots < K) stg.issue(slot, ent_var_row(p, pick[j + kSlots], stride), sub);
+        if (j + kSlots < Kw) stg.issue(slot, ent_var_row(p, pick[j + kSlots], stride), sub);
         cp_async_commit();
         slot = (slot + 1 == kSlots) ? 0 : slot + 1;
 #pragma unroll

@@ -272,3 +272,58 @@ extern "C" int mke_neg_keep_owned(int32_t* neg_ent, int32_t n, int32_t K, int32_
   MKE_CHECK_LAUNCH("neg_keep_owned_kernel");
   return 0;
 }
+
+// ---- the same, COMPACTED: this rank's negatives first (in their original order), then dummies ------------------
+// neg_valid[i] = low_ones(count) and the side word is permuted along, so that bit j still belongs to slot j.  The
+// one-wave phase-1 kernel then stops its K-loop at the longest list of a warp's four positives
+// (mke_rel_step_structured4 with compact = 1): at 8 ranks a positive keeps 2.5 of its 10 negatives on average.
+namespace mke {
+__global__ void neg_keep_owned_compact_kernel(int32_t* __restrict__ neg_ent, uint32_t* __restrict__ neg_side, int n, int K,
+                                              ShardMap smap, int my_shard, int32_t dummy_id,
+                                              uint32_t* __restrict__ neg_valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t* row = neg_ent + (size_t)i * K;
+  const uint32_t side = neg_side[i];
+  uint32_t new_side = 0u;
+  int cnt = 0;
+  for (int j = 0; j < K; ++j) {
+    const int32_t e = row[j];
+    int s;
+    int32_t l;
+    smap.locate(e, s, l);
+    if (s == my_shard) {
+      row[cnt] = e;  // cnt <= j: never overwrites an entry not yet read
+      new_side |= ((side >> j) & 1u) << cnt;
+      ++cnt;
+    }
+  }
+  for (int j = cnt; j < K; ++j) row[j] = dummy_id;
+  neg_side[i] = new_side;
+  neg_valid[i] = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+}
+}  // namespace mke
+
+extern "C" int mke_neg_keep_owned2(int32_t* neg_ent, uint32_t* neg_side, int32_t n, int32_t K, int32_t n_shards,
+                                   int32_t shard_split, int32_t my_shard, int32_t dummy_id, uint32_t* neg_valid,
+                                   mke_stream_t stream) {
+  MKE_CHECK_ARG(n >= 0 && K >= 1 && K <= MKE_MAX_NEG, "bad n / K");
+  MKE_CHECK_ARG(n_shards == 2 || n_shards == 4 || n_shards == 8, "n_shards=%d (2, 4 or 8)", n_shards);
+  MKE_CHECK_ARG(my_shard >= 0 && my_shard < n_shards && shard_split >= 0, "bad shard / split");
+  if (n == 0) return 0;
+  MKE_CHECK_ARG(neg_ent && neg_side && neg_valid, "null pointer");
+  mke_table_t t{};
+  t.n_shards = n_shards;
+  t.shard_split = shard_split;
+  const mke::ShardMap smap = mke::shard_map(&t);
+  {
+    int s;
+    int32_t l;
+    smap.locate(dummy_id, s, l);
+    MKE_CHECK_ARG(s == my_shard, "dummy row %d does not live on shard %d", dummy_id, my_shard);
+  }
+  mke::neg_keep_owned_compact_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(neg_ent, neg_side, n, K, smap,
+                                                                                       my_shard, dummy_id, neg_valid);
+  MKE_CHECK_LAUNCH("neg_keep_owned_compact_kernel");
+  return 0;
+}

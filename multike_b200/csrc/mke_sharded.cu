@@ -258,8 +258,8 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
                                           v->neg_ent[buf], v->neg_side[buf], st))
       return rc;
     if (v->owner_negs)
-      return mke_neg_keep_owned(v->neg_ent[buf], p.l1 + p.l2, v->K, v->world, v->ent->shard_split, v->rank,
-                                v->dummy_row, v->neg_valid[buf], st);
+      return mke_neg_keep_owned2(v->neg_ent[buf], v->neg_side[buf], p.l1 + p.l2, v->K, v->world, v->ent->shard_split,
+                                 v->rank, v->dummy_row, v->neg_valid[buf], st);
     return 0;
   };
   long long positives = 0;
@@ -274,8 +274,8 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
     if (have_next) nxt = make_plan(v, (first_step + s + 1) % steps_per_epoch);
     if (n > 0) {
       const bool timed = timer_begin(main);
-      rc = mke_rel_step_structured3(v->ent, v->rel, cur.p1, cur.l1, cur.p2, cur.l2, v->K, v->neg_ent[buf],
-                                    v->neg_side[buf], v->owner_negs ? v->neg_valid[buf] : nullptr, cur.lo, cur.hi,
+      rc = mke_rel_step_structured4(v->ent, v->rel, cur.p1, cur.l1, cur.p2, cur.l2, v->K, v->neg_ent[buf],
+                                    v->neg_side[buf], v->owner_negs ? v->neg_valid[buf] : nullptr, 1, cur.lo, cur.hi,
                                     nullptr, 1.0f, v->step_loss + s, v->variant, main);
       if (timed) timer_end(main);
       if (rc) break;

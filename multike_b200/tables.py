@@ -254,15 +254,29 @@ def neg_keep_owned(neg_ent, K, n_shards, shard_split, my_shard, dummy_id):
     return valid
 
 
-def rel_step_owned(ent, rel, pos, neg_ent, neg_side, neg_valid, own_lo, own_hi, K, loss_accum, variant=0):
-    """mke_rel_step_structured3: one rank's share of a step under "negatives where they live"."""
+def neg_keep_owned_compact(neg_ent, neg_side, K, n_shards, shard_split, my_shard, dummy_id):
+    """mke_neg_keep_owned2: in place (ids AND side words); this rank's negatives first; returns the masks
+    low_ones(count) [n]."""
+    lib = _cabi.load()
+    n = neg_ent.numel() // K
+    valid = torch.empty(n, dtype=torch.int32, device=neg_ent.device)
+    _cabi.check(lib.mke_neg_keep_owned2(neg_ent.data_ptr(), neg_side.data_ptr(), n, int(K), int(n_shards),
+                                        int(shard_split), int(my_shard), int(dummy_id), valid.data_ptr(),
+                                        _cabi.current_stream()))
+    return valid
+
+
+def rel_step_owned(ent, rel, pos, neg_ent, neg_side, neg_valid, own_lo, own_hi, K, loss_accum, variant=0, compact=False):
+    """mke_rel_step_structured4: one rank's share of a step under "negatives where they live" (compact: the
+    batch went through neg_keep_owned_compact)."""
     lib = _cabi.load()
     dev = ent.device
     pos, neg_ent = _i32(pos, dev), _i32(neg_ent, dev)
     n = pos.numel() // 3
-    _cabi.check(lib.mke_rel_step_structured3(ent.c, rel.c, _cabi.ptr(pos), n, None, 0, int(K), _cabi.ptr(neg_ent),
-                                             _cabi.ptr(neg_side), _cabi.ptr(neg_valid), int(own_lo), int(own_hi),
-                                             None, 1.0, _cabi.ptr(loss_accum), int(variant), _cabi.current_stream()))
+    _cabi.check(lib.mke_rel_step_structured4(ent.c, rel.c, _cabi.ptr(pos), n, None, 0, int(K), _cabi.ptr(neg_ent),
+                                             _cabi.ptr(neg_side), _cabi.ptr(neg_valid), int(bool(compact)), int(own_lo),
+                                             int(own_hi), None, 1.0, _cabi.ptr(loss_accum), int(variant),
+                                             _cabi.current_stream()))
 
 
 def apply_adagrad(table, acc, lr):

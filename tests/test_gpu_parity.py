@@ -539,9 +539,9 @@ def test_full_size_row_stream_schedule_equals_one_wave_kernel(G, full):
     torch.testing.assert_close(a[5], b[5], rtol=0, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant,compact", [(0, False), (3, False), (0, True), (3, True)])
 @pytest.mark.parametrize("world", [4, 8])
-def test_negatives_where_they_live_decomposition(G, full, world, variant):
+def test_negatives_where_they_live_decomposition(G, full, world, variant, compact):
     """mke_neg_keep_owned + mke_rel_step_structured3 (the multi-GPU scheme of sharded.py, run here as
     `world` launches into ONE table): every virtual rank walks all positives of its KG but scores only
     the negatives whose entity it would own, and the positive terms of its slice of the batch; the sum
@@ -567,15 +567,29 @@ def test_negatives_where_they_live_decomposition(G, full, world, variant):
         ne = (neg_ent[:B1] if first else neg_ent[B1:]).clone()
         ns = (neg_side[:B1] if first else neg_side[B1:]).contiguous()
         dummy = rank if first else split + (rank - half)
-        valid = T.neg_keep_owned(ne, K, world, split, rank, dummy)
-        # the mask is exactly "owner == rank", and foreign slots now hold the dummy row
-        owner, _ = shard_owner((neg_ent[:B1] if first else neg_ent[B1:]).cpu().numpy(), world, split)
-        bits = ((valid.cpu().numpy().astype(np.int64)[:, None] >> np.arange(K)) & 1).astype(bool)
-        assert np.array_equal(bits, owner == rank)
-        assert bool((ne.cpu().numpy()[~bits] == dummy).all())
+        orig = (neg_ent[:B1] if first else neg_ent[B1:]).cpu().numpy().reshape(-1, K)
+        owner, _ = shard_owner(orig, world, split)
+        if compact:  # mke_neg_keep_owned2: this rank's negatives first, in their order; side bits travel along
+            ns = ns.clone()
+            side0 = ns.cpu().numpy().view(np.uint32).astype(np.int64)
+            valid = T.neg_keep_owned_compact(ne, ns, K, world, split, rank, dummy)
+            cnt = (owner == rank).sum(1)
+            assert np.array_equal(valid.cpu().numpy().view(np.uint32).astype(np.int64), (1 << cnt) - 1)
+            got, side1 = ne.cpu().numpy().reshape(-1, K), ns.cpu().numpy().view(np.uint32).astype(np.int64)
+            for row in (0, 1, 17, len(orig) - 1):
+                keep = np.flatnonzero(owner[row] == rank)
+                assert np.array_equal(got[row, :len(keep)], orig[row, keep]) and (got[row, len(keep):] == dummy).all()
+                assert side1[row] == sum(((side0[row] >> j) & 1) << k for k, j in enumerate(keep))
+            bits = np.arange(K)[None, :] < cnt[:, None]
+        else:
+            valid = T.neg_keep_owned(ne, K, world, split, rank, dummy)
+            # the mask is exactly "owner == rank", and foreign slots now hold the dummy row
+            bits = ((valid.cpu().numpy().astype(np.int64)[:, None] >> np.arange(K)) & 1).astype(bool)
+            assert np.array_equal(bits, owner == rank)
+            assert bool((ne.cpu().numpy().reshape(-1, K)[~bits] == dummy).all())
         kept += int(bits.sum())
         lo, hi = rank_range(len(pos), rank % half, half)
-        T.rel_step_owned(ent, rel, pos, ne, ns, valid, lo, hi, K, acc, variant=variant)
+        T.rel_step_owned(ent, rel, pos, ne, ns, valid, lo, hi, K, acc, variant=variant, compact=compact)
     assert kept == (B1 + B2) * K
     assert U.loss_value(acc) == pytest.approx(want[0], rel=1e-6)
     torch.testing.assert_close(ent.grad_sum(), want[1], rtol=1e-4, atol=2e-5)
