@@ -456,6 +456,18 @@ int mke_rel_step_structured3(const mke_table_t* ent, const mke_table_t* rel,
 /* ------------------------------------------------------------------------------------------
  * Peer memory for row-sharded tables (one process per GPU; handles travel over torch.distributed).
  * ------------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core GEMM of the literal auto-encoder (code/literal_encoder.py:45-69: six affine layers, forward and
+ * backward) -- hand-written tcgen05 / TMA / TMEM kernel at fp32-equivalent precision (3xTF32 split).
+ *   C[M,N] (ldc) = A[M,K] . B[N,K]^T (+ bias[N])     A, B row-major with K contiguous
+ * Operands are passed as (hi, lo) pairs produced by mke_split_tf32 (hi: low 13 mantissa bits cleared, lo = x - hi);
+ * lda / ldb multiples of 4 floats, base pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+int mke_split_tf32(const float* x, float* hi, float* lo, int64_t n, mke_stream_t stream);
+int mke_gemm_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
+                    int64_t ldb, int32_t M, int32_t N, int32_t K, const float* bias_or_null, float* C,
+                    int64_t ldc, mke_stream_t stream);
+
 /* mke_neg_keep_owned, COMPACTED: this rank's negatives first (original order), dummies behind, the side word
  * permuted along; neg_valid[i] = low_ones(count).  With compact = 1 mke_rel_step_structured4 (otherwise
  * mke_rel_step_structured3) lets the one-wave kernel (variant 0) stop its K-loop at the longest list of a warp's

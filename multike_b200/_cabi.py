@@ -118,6 +118,8 @@ SIGNATURES = {
     "mke_rel_train_steps": (_i32, [_c.POINTER(MkeRelView), _i32, _i32, _u64, _c.POINTER(_c.c_int64), _vp, _vp]),
     "mke_rel_sharded_train_steps": (_i32, [_c.POINTER(MkeRelShardedView), _i32, _i32, _u64, _c.POINTER(_c.c_uint32),
                                            _c.POINTER(_c.c_int64), _vp, _vp]),
+    "mke_split_tf32": (_i32, [_vp, _vp, _vp, _c.c_int64, _vp]),
+    "mke_gemm_tf32x3": (_i32, [_vp, _vp, _c.c_int64, _vp, _vp, _c.c_int64, _i32, _i32, _i32, _vp, _vp, _c.c_int64, _vp]),
     "mke_rel_persist_workspace_bytes": (_c.c_int64, [_i32, _i32, _i32, _i32]),
     "mke_attr_cnn_param_count": (_c.c_int64, [_i32]),
     "mke_attr_cnn_workspace_floats": (_c.c_int64, [_i32, _i32]),

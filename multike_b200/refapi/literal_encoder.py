@@ -1,11 +1,14 @@
 """Mirror of AutoEncoderModel (code/literal_encoder.py:19-144): the literal auto-encoder
 1500 -> 1024 -> 512 -> dim -> 512 -> 1024 -> 1500, the only true GEMMs of the pipeline.
 
-Same constructor and methods as the reference.  The six affine layers are plain dense GEMMs and run
-on the tensor cores through cuBLAS (torch.matmul, TF32 inputs / fp32 accumulate by default;
-`args.encoder_tf32 = False` keeps full fp32).  All weights and biases live in ONE flat fp32 CUDA
-vector whose Adagrad update is the hand-written dense kernel mke_dense_apply_adagrad
-(acc0 = 0.1, no epsilon [TF semantics]).  No CPU path.
+Same constructor and methods as the reference.  The six affine layers are plain dense GEMMs: forward, input
+gradients and weight gradients (17 products per step) run on the hand-written tcgen05 / TMA / TMEM kernel of
+csrc/mke_gemm.cu (multike_b200/gemm.py) at fp32-equivalent precision (3xTF32 split, chunked accumulation); the
+chain rule between them (activation, global l2-norm of the code, squared error) is written out below -- no
+autograd.  `args.encoder_gemm = "cublas"` runs the same step on torch.matmul in full fp32 instead: the timed
+baseline of tools/bench_autoencoder.py.  All weights and biases live in ONE flat fp32 CUDA vector whose Adagrad
+update is the hand-written dense kernel mke_dense_apply_adagrad (acc0 = 0.1, no epsilon [TF semantics]).
+No CPU path.
 """
 import sys as _sys
 
@@ -18,6 +21,7 @@ import numpy as np
 import torch
 
 from multike_b200 import _cabi
+from multike_b200 import gemm as _gemm
 from multike_b200.tables import ADAGRAD_INIT
 
 
@@ -53,7 +57,8 @@ class AutoEncoderModel:
             hidden_dimensions = [1024, 512, self.args.dim]
         self.hidden_dimensions = list(hidden_dimensions)
         self.layer_num = len(self.hidden_dimensions)
-        self.tf32 = bool(getattr(args, "encoder_tf32", True))
+        self.gemm = str(getattr(args, "encoder_gemm", "tcgen05"))   # "tcgen05" (ours) | "cublas" (fp32 baseline)
+        assert self.gemm in ("tcgen05", "cublas")
         data = torch.as_tensor(np.reshape(np.asarray(word_vec_list, dtype=np.float32),
                                           [len(word_vec_list), input_dimension])).to(self.device)
         if self.args.encoder_normalize:  # sklearn.preprocessing.normalize: unit l2 rows (:34-35)
@@ -94,23 +99,64 @@ class AutoEncoderModel:
             x = _act(x @ params[2 * (self.layer_num + i)] + params[2 * (self.layer_num + i) + 1], self.args.encoder_active)
         return x
 
+    # -- one training step, chain rule written out ------------------------------------------------
+    def _nt(self, a, b, bias=None):
+        """a [M, K] . b [N, K]^T (+ bias): the tensor-core kernel, or fp32 cuBLAS as the baseline"""
+        if self.gemm == "tcgen05":
+            return _gemm.gemm_nt(a, b, bias)
+        out = a @ b.t()
+        return out if bias is None else out + bias
+
+    def _act_grad(self, y, g):
+        kind = self.args.encoder_active
+        if kind == 'sigmoid':
+            return g * y * (1 - y)
+        if kind == 'tanh':
+            return g * (1 - y * y)
+        return g
+
     def _step(self, batch):
         """one session.run([loss, optimizer]) (:62-69): mean squared reconstruction error, Adagrad"""
         prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.tf32
+        if self.gemm == "cublas":
+            torch.backends.cuda.matmul.allow_tf32 = False
         try:
-            leaves = [p.detach().requires_grad_(True) for p in self.params]
-            code = self.encoder(batch, leaves)
-            if self.args.encoder_normalize:  # tf.nn.l2_normalize without axis: global norm (:66)
-                code = code * torch.rsqrt(torch.clamp((code * code).sum(), min=1e-12))
-            loss = ((self.decoder(code, leaves) - batch) ** 2).mean()
-            grads = torch.autograd.grad(loss, leaves)
+            n_l, P = self.layer_num, self.params
+            # forward: layers 0 .. L-1 encode, L .. 2L-1 decode; acts[i] = input of layer i
+            acts, x, code, inv = [batch], batch, None, None
+            for i in range(2 * n_l):
+                x = _act(self._nt(x, P[2 * i].t().contiguous(), P[2 * i + 1]), self.args.encoder_active)
+                if i == n_l - 1 and self.args.encoder_normalize:  # tf.nn.l2_normalize without axis: global norm (:66)
+                    code = x
+                    inv = torch.rsqrt(torch.clamp((code * code).sum(), min=1e-12))
+                    x = code * inv
+                acts.append(x)
+            diff = acts[-1] - batch
+            loss = (diff * diff).mean()
+            # backward
+            g = diff * (2.0 / diff.numel())
+            off_end = self.theta.numel()
+            for i in reversed(range(2 * n_l)):
+                if i == n_l - 1 and code is not None:
+                    # y = c r, r = rsqrt(max(S, eps)), S = sum c^2: dc = g r - c r^3 (g . c) while S >= eps
+                    dot = (g * code).sum()
+                    below = (code * code).sum() < 1e-12
+                    g = g * inv - torch.where(below, torch.zeros_like(dot), dot * inv ** 3) * code
+                    g = self._act_grad(code, g)
+                else:
+                    g = self._act_grad(acts[i + 1], g)
+                w, b = P[2 * i], P[2 * i + 1]
+                off_b = off_end - b.numel()
+                off_w = off_b - w.numel()
+                self.grad[off_b:off_end].copy_(g.sum(0))
+                # dW [in, out] = X^T [in, B] . (dY^T [out, B])^T
+                dw = self._nt(acts[i].t().contiguous(), g.t().contiguous())
+                self.grad[off_w:off_b].copy_(dw.reshape(-1))
+                if i > 0:
+                    g = self._nt(g, w)   # dX [B, in] = dY [B, out] . (W [in, out])^T
+                off_end = off_w
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
-        off = 0
-        for g in grads:
-            self.grad[off:off + g.numel()].copy_(g.reshape(-1))
-            off += g.numel()
         _cabi.check(self._lib.mke_dense_apply_adagrad(self.theta.data_ptr(), self.grad.data_ptr(), self.acc.data_ptr(),
                                                       self.theta.numel(), float(self.args.learning_rate),
                                                       _cabi.current_stream()))

@@ -274,10 +274,11 @@ def test_multike_truncated_neighbours_are_used(golden):
         MultiKE(m.data, types.SimpleNamespace(alignment_module='mapping', output='', training_data='x'), None)
 
 
-@pytest.mark.parametrize("tf32,tol", [(False, 1e-5), (True, 2e-3)])
-def test_literal_autoencoder_matches_oracle(tf32, tol, capsys):
-    """AutoEncoderModel (literal_encoder.py:19-144): GEMMs on the tensor cores through cuBLAS, the
-    Adagrad update on the hand-written dense kernel; two epochs against the float64 oracle."""
+@pytest.mark.parametrize("gemm,tol", [("tcgen05", 1e-5), ("cublas", 1e-5)])
+def test_literal_autoencoder_matches_oracle(gemm, tol, capsys):
+    """AutoEncoderModel (literal_encoder.py:19-144): all GEMMs on the hand-written tcgen05 kernel at
+    fp32-equivalent precision (default) or on fp32 cuBLAS (the baseline), chain rule written out, Adagrad on the
+    hand-written dense kernel; two epochs against the float64 oracle at ONE tolerance for both."""
     from multike_b200.refapi.literal_encoder import AutoEncoderModel
     from oracle import autoencoder as oa
     rng = np.random.default_rng(0)
@@ -285,7 +286,7 @@ def test_literal_autoencoder_matches_oracle(tf32, tol, capsys):
     data = rng.normal(0, 1, (n, d_in))
     init = [rng.normal(0, 1, s) for s in oa.shapes(d_in, hidden)]
     args = types.SimpleNamespace(dim=16, encoder_normalize=True, encoder_active="thah", learning_rate=0.01, batch_size=50,
-                                 encoder_tf32=tf32)
+                                 encoder_gemm=gemm)
     m = AutoEncoderModel(data, args, input_dimension=d_in, hidden_dimensions=list(hidden), init_params=init)
     o = oa.AutoEncoderOracle(init, 3, active="thah", normalize=True, lr=0.01)
     rows = data / np.linalg.norm(data, axis=1, keepdims=True)
@@ -298,7 +299,7 @@ def test_literal_autoencoder_matches_oracle(tf32, tol, capsys):
         np.testing.assert_allclose(p.cpu().numpy(), q.numpy(), rtol=0, atol=50 * tol)
     enc = m.encoder_multi_batches(data)
     want_enc = o.encode(data)   # values of order 1e2 (N(0,1) weights): tolerance relative to the largest code
-    np.testing.assert_allclose(enc, want_enc, rtol=0, atol=(1e-3 if tf32 else 1e-5) * np.abs(want_enc).max())
+    np.testing.assert_allclose(enc, want_enc, rtol=0, atol=1e-5 * np.abs(want_enc).max())
     assert set(m.weights) == {"encoder_h0", "encoder_h1", "encoder_h2", "decoder_h0", "decoder_h1", "decoder_h2"}
 
 
