@@ -240,6 +240,24 @@ int mke_align_fwd_bwd(const mke_table_t* shared, const mke_table_t* name, const 
                       float scale, double* loss_accum, mke_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SSL space-mapping step: _define_space_mapping_graph + train_shared_space_mapping_1epo
+ * (MultiKE_model.py:241-261, :439-454), space_mapping_loss / orthogonal_loss (losses.py:53-63).
+ *   loss += sum over the views X in {name, rv, av} of
+ *           |F - gl2n(X M_X)|^2 + orthogonal_weight |M_X M_X^T - I|^2 + norm_w |M_X|^2
+ * gl2n = l2_normalize over the WHOLE batch (tf.nn.l2_normalize without axis); every table is read through its
+ * normalised view at the ids idx[0..n).  Outputs: gradient rows of the shared table (accumulated into shared->grad,
+ * rows flagged; the view tables do not train: MultiKE_model.py:257) and maps_grad [3][dim][dim] (overwritten) for
+ * maps [3][dim][dim] (row-major, order name, rv, av).  workspace: mke_space_mapping_workspace_floats(n, dim) floats,
+ * 8-byte aligned.  Three launches (rows -> products and batch-wide sums; one block: the dim x dim algebra; rows ->
+ * gradient rows), no host sync.
+ * ------------------------------------------------------------------------------------------ */
+int64_t mke_space_mapping_workspace_floats(int32_t n, int32_t dim);
+int mke_space_mapping_fwd_bwd(const mke_table_t* shared, const mke_table_t* name, const mke_table_t* rv,
+                              const mke_table_t* av, const int32_t* idx, int32_t n, const float* maps,
+                              float* maps_grad, float orthogonal_weight, float norm_w, float* workspace,
+                              double* loss_accum, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * losses.py as free functions on already gathered [n, dim] matrices (row stride ld floats).
  * ------------------------------------------------------------------------------------------ */
 

@@ -126,6 +126,8 @@ SIGNATURES = {
     "mke_attr_cnn_fwd_bwd": (_i32, [_PT, _PT, _PT, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mke_dense_apply_adagrad": (_i32, [_vp, _vp, _vp, _c.c_int64, _f32, _vp]),
     "mke_align_fwd_bwd": (_i32, [_PT, _PT, _PT, _PT, _vp, _i32, _f32, _f32, _vp, _vp]),
+    "mke_space_mapping_workspace_floats": (_c.c_int64, [_i32, _i32]),
+    "mke_space_mapping_fwd_bwd": (_i32, [_PT, _PT, _PT, _PT, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp]),
     "mke_dense_logistic_fwd_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "mke_dense_sqdist_fwd_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mke_timing_enable": (_i32, [_i32]),

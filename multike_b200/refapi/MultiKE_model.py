@@ -243,8 +243,9 @@ class MultiKE:
     # --- SSL late combination (MultiKE_model.py:241-261, :439-454) --------------------------------
     def _define_space_mapping_graph(self):
         """Only variables whose name starts with "shared" train (:257): ent_embeds and the three
-        dim x dim mappings (tf.initializers.orthogonal(), gain 1).  The 75x75 products are plain
-        library GEMMs (cuBLAS via torch); gradient rows and both Adagrad updates use the kernels."""
+        dim x dim mappings (tf.initializers.orthogonal(), gain 1).  The whole step -- gathers, the three
+        [batch, dim] x [dim, dim] products, the batch-wide norms, M M^T - I and every gradient -- is
+        mke_space_mapping_fwd_bwd (csrc/mke_space.cu); both Adagrad updates use the apply kernels."""
         assert self.name_embeds is not None, "the space-mapping graph needs data.local_name_vectors"
         from multike_b200.refapi import losses as L
         self._sm_losses = L
@@ -270,23 +271,22 @@ class MultiKE:
         batch_size = self.args.entity_batch_size if steps > 1 else n
         lr, ow = self.args.learning_rate, self.args.orthogonal_weight
         F_tab = self.ent_embeds
-        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        total = torch.zeros(1, dtype=torch.float64, device=self.device)
+        dim = F_tab.dim
+        ws = torch.empty(int(lib.mke_space_mapping_workspace_floats(batch_size, dim)), dtype=torch.float32,
+                         device=self.device)
         for _ in range(steps):
-            idx = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()
-            final = F_tab.export(idx).requires_grad_(True)
-            views = (self.name_embeds.export(idx), self._rv.ent.export(idx), self.av_ent_embeds.export(idx))
-            maps = self._maps.detach().clone().requires_grad_(True)
-            loss = sum(self._sm_losses.space_mapping_loss(x, final, maps[k], self.eye_mat, ow) for k, x in enumerate(views))
-            g_final, g_maps = torch.autograd.grad(loss, [final, maps])
-            F_tab.grad[:, : F_tab.dim].index_add_(0, idx.long(), g_final)   # ids are distinct (random.sample)
-            if F_tab.touched is not None:
-                F_tab.touched[idx.long()] = 1
+            idx = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()  # random.sample: distinct ids
+            # forward + backward of the three mapping losses in three launches (csrc/mke_space.cu): gradient rows
+            # of the shared table and the three mapping gradients; only `shared*` variables train (:257)
+            _cabi.check(lib.mke_space_mapping_fwd_bwd(
+                F_tab.c, self.name_embeds.c, self._rv.ent.c, self.av_ent_embeds.c, idx.data_ptr(), idx.numel(),
+                self._maps.data_ptr(), self._maps_grad.data_ptr(), float(ow), 0.0001, ws.data_ptr(), total.data_ptr(),
+                _cabi.current_stream()))
             F_tab.apply_adagrad(self._sm_slot, lr)
-            self._maps_grad.copy_(g_maps)
             _cabi.check(lib.mke_dense_apply_adagrad(self._maps.data_ptr(), self._maps_grad.data_ptr(),
                                                     self._maps_acc.data_ptr(), self._maps.numel(), float(lr),
                                                     _cabi.current_stream()))
-            total += loss.detach().double()
         epoch_loss = float(total) / max(steps * batch_size, 1)
         print('epoch {} of shared space learning, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss,
                                                                                            time.time() - start))
