@@ -304,7 +304,7 @@ typedef struct mke_rel_view {
   uint64_t seed;
   int32_t*  neg_ent[2];            /* [batch_size*K] x2, or NULL => negatives drawn inside phase 1 */
   uint32_t* neg_side[2];           /* [batch_size]   x2                                         */
-  double* step_loss;               /* device [>= n_steps]: loss of step s is ADDED to step_loss[s] */
+  double* step_loss;               /* device [>= n_steps]: mke_rel_train_steps zeroes [0, n_steps) and leaves the loss of step s in step_loss[s] */
   double* host_step_loss;          /* pinned host [>= n_steps] or NULL: step_loss[s] is copied
                                       here (async, 8 bytes) after every step                    */
   int32_t variant;                 /* phase-1 schedule; 4 = persistent step kernel (below)         */
@@ -513,6 +513,11 @@ int mke_ipc_close(void* ptr);
  * 31-33; a zero row stays zero).  Sims are fp32 inner products accumulated in ascending column
  * order of the embedding (one fmaf chain per pair), so bit-equal rows give bit-equal sims.
  * ------------------------------------------------------------------------------------------ */
+
+/* Which implementation mke_sim_rank / mke_sim_topk run: 1 (default) = tcgen05 tiles at fp32-equivalent precision
+ * (3xTF32 split, csrc/mke_sim_tc.cu), 0 = the fp32 FMA tiles of csrc/mke_sim.cu (the measured baseline).  on < 0 only
+ * queries.  Returns the previous setting.  The same tie rules hold for both (equal rows give bit-equal sims). */
+int mke_sim_use_tensor_cores(int32_t on);
 
 /* floats of workspace mke_sim_rank needs (prepared copies of both row sets + per-row scratch) */
 int64_t mke_sim_rank_workspace_floats(int32_t n1, int32_t n2, int32_t dim);

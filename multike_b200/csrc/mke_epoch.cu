@@ -174,12 +174,13 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
       const Slice sl = step_slice(v, (q.first_step + k) % steps_per_epoch);
       positives += sl.len1 + sl.len2;
     }
-    if (host_fed) {
-      int32_t* s1 = (int32_t*)(ws + L.stage1[buf]);
-      int32_t* s2 = (int32_t*)(ws + L.stage2[buf]);
-      uint32_t* fl = (uint32_t*)(ws + L.flags[buf]);
-      if (done[buf] != nullptr) cudaStreamWaitEvent(side, done[buf], 0);  // the launch that last read this buffer
-      for (int k = 0; k < len; ++k) {
+    // Host fed: the batches of this launch travel on `side` while the kernel runs; the kernel waits for flags[k]
+    // before it reads step k.  Only step 0 is copied before the launch (the kernel's prologue needs it), the other
+    // steps after it, so that a short run does not wait for len x 3 copy calls before its kernel starts.
+    int32_t *s1 = nullptr, *s2 = nullptr;
+    uint32_t* fl = nullptr;
+    auto copy_steps = [&](int k0, int k1) -> cudaError_t {
+      for (int k = k0; k < k1; ++k) {
         const Slice sl = step_slice(v, (q.first_step + k) % steps_per_epoch);
         cudaError_t e = cudaSuccess;
         if (sl.len1 > 0)
@@ -190,8 +191,16 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
                               cudaMemcpyHostToDevice, side);
         if (e == cudaSuccess)  // lands after the batch (stream order): "step k is here"
           e = cudaMemcpyAsync(fl + k, v->persist_flag_src + (seq & 255u), sizeof(uint32_t), cudaMemcpyHostToDevice, side);
-        if (e != cudaSuccess) return cuda_fail(e, "H2D batch");
+        if (e != cudaSuccess) return e;
       }
+      return cudaSuccess;
+    };
+    if (host_fed) {
+      s1 = (int32_t*)(ws + L.stage1[buf]);
+      s2 = (int32_t*)(ws + L.stage2[buf]);
+      fl = (uint32_t*)(ws + L.flags[buf]);
+      if (done[buf] != nullptr) cudaStreamWaitEvent(side, done[buf], 0);  // the launch that last read this buffer
+      if (cudaError_t e = copy_steps(0, 1)) return cuda_fail(e, "H2D batch");
       q.t1 = q.t2 = nullptr;
       q.st1 = s1;
       q.st2 = s2;
@@ -218,6 +227,8 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
     const bool timed = g_timer.used + 2 <= (int)g_timer.ev.size() && (g_timer.seen++ % g_timer.every) == 0;
     if (timed) cudaEventRecord(g_timer.ev[g_timer.used], main);
     const int rc = launch_rel_persist(p, q, main);
+    if (rc == 0 && host_fed)
+      if (cudaError_t e = copy_steps(1, len)) return cuda_fail(e, "H2D batch");
     if (bt_buf != nullptr) {
       cudaStreamSynchronize(main);
       std::vector<unsigned long long> host(bt_words + 2);
@@ -238,6 +249,7 @@ static int train_steps_persistent(const mke_rel_view_t* v, int first_step, int n
       MKE_CHECK_ARG(rc < 0 || c0 == 0, "persistent launch shape changed between chunks");
       return rc;
     }
+
     if (host_fed) {
       done[buf] = pool.get();
       cudaEventRecord(done[buf], main);
@@ -276,6 +288,9 @@ extern "C" int mke_rel_train_steps(const mke_rel_view_t* v, int32_t first_step, 
   MKE_CHECK_ARG(!host_fed || ((v->n1 == 0 || (v->host_triples1 && v->stage1[0] && v->stage1[1])) &&
                               (v->n2 == 0 || (v->host_triples2 && v->stage2[0] && v->stage2[1]))),
                 "host-fed batches need pinned triples and two staging buffers per KG");
+  if (n_steps > 0)  // every step ADDS its loss to step_loss[s]
+    if (cudaError_t e = cudaMemsetAsync(v->step_loss, 0, sizeof(double) * (size_t)n_steps, (cudaStream_t)main_))
+      return cuda_fail(e, "memset step_loss");
   if (v->variant == 4) {  // persistent step kernel; shapes it does not cover run one launch per phase (variant 3)
     const int rc = train_steps_persistent(v, first_step, n_steps, first_global_step, host_fed, positives_out,
                                           (cudaStream_t)main_, (cudaStream_t)side_);

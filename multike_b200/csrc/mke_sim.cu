@@ -9,12 +9,14 @@
 //                    the k most similar rows of every row, straight into the table the on-device
 //                    sampler reads (mke_kg_sampler_t.neighbours).
 //
-// The contraction is 75..128 deep and has to order near-ties like the reference's fp32 sgemm, so
-// it runs on the fp32 FMA pipe (no tensor cores: tf32/bf16 would reorder the ranks): one thread
+// Two implementations of the contraction.  DEFAULT: tcgen05 tiles at fp32-equivalent precision (3xTF32) with the
+// consumers fused into the TMEM epilogue -- mke_sim_tc.cu.  BASELINE (mke_sim_use_tensor_cores(0) / MKE_SIM_TC=0),
+// the kernels of this file: fp32 FMA pipe, one thread
 // block owns a 128-row tile of A, streams 128-row tiles of B through a double-buffered cp.async
 // stage and keeps an 8 x 4 block of sims per thread in registers.  Every sim is the sum of two fmaf
 // chains in ascending k (even and odd columns, packed FFMA2) -- the same two chains
 // sim_gold_kernel uses -- so equal rows give bit-equal sims and the tie rules below are exact.
+#include <cstdlib>
 #include "mke_common.cuh"
 
 namespace mke {
@@ -410,15 +412,38 @@ static int sim_prepare(const float* src, const int32_t* idx, int n, int stride, 
   return 0;
 }
 
+// mke_sim_tc.cu: the same searches on the tensor cores (default; MKE_SIM_TC=0 selects the fp32 FMA tiles above, kept
+// as the measured baseline)
+int sim_tc_ws(int dim);
+int sim_rank_tc(const float* emb1, const int32_t* idx1, int n1, const float* emb2, const int32_t* idx2, int n2, int stride,
+                int dim, int normalize, const int32_t* gold, float* workspace, int32_t* rank_out, int32_t* top1_out,
+                unsigned long long** best_out, cudaStream_t stream);
+int sim_store_tc(const float* hi, const float* lo, int n, int ws, int row_base, int rows, float* out, size_t pitch,
+                 cudaStream_t stream);
+int sim_prepare_tc(const float* src, const int32_t* idx, int n, int stride, int dim, int normalize, float* hi, float* lo,
+                   cudaStream_t stream);
+static int g_sim_tc = -1;  // -1: not decided yet (MKE_SIM_TC, default on)
+static bool sim_use_tc() {
+  if (g_sim_tc < 0) g_sim_tc = getenv("MKE_SIM_TC") ? (atoi(getenv("MKE_SIM_TC")) != 0) : 1;
+  return g_sim_tc != 0;
+}
+
 }  // namespace mke
 
 using namespace mke;
 
+extern "C" int mke_sim_use_tensor_cores(int32_t on) {
+  const int prev = sim_use_tc() ? 1 : 0;
+  if (on >= 0) g_sim_tc = on != 0;
+  return prev;
+}
+
 extern "C" int64_t mke_sim_rank_workspace_floats(int32_t n1, int32_t n2, int32_t dim) {
   if (n1 < 0 || n2 < 0 || dim <= 0) return -1;
   const int64_t ws = sim_ws(dim);
-  // prepared A, prepared B, gold scores, packed (score, column) arg-max keys (8 bytes each)
-  return (int64_t)n1 * ws + (int64_t)n2 * ws + ((n1 + 1) & ~1) + 2 * (int64_t)n1 + 8;
+  // prepared A and B as TF32 part + remainder, the gathered gold rows of B likewise, gold scores, packed (score,
+  // column) arg-max keys (8 bytes each)
+  return 4 * (int64_t)n1 * ws + 2 * (int64_t)n2 * ws + ((n1 + 1) & ~1) + 2 * (int64_t)n1 + 8;
 }
 
 extern "C" int mke_sim_rank(const float* emb1, const int32_t* idx1_or_null, int32_t n1, const float* emb2,
@@ -434,6 +459,15 @@ extern "C" int mke_sim_rank(const float* emb1, const int32_t* idx1_or_null, int3
   MKE_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "workspace must be 16-byte aligned");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int ws = sim_ws(dim);
+  if (sim_use_tc()) {
+    unsigned long long* best_tc = nullptr;
+    if (int rc = sim_rank_tc(emb1, idx1_or_null, n1, emb2, idx2_or_null, n2, stride, dim, normalize, gold_or_null, workspace,
+                             rank_out, top1_out, &best_tc, stream))
+      return rc;
+    sim_finish_kernel<<<(n1 + 255) / 256, 256, 0, stream>>>(best_tc, n1, top1_out);
+    MKE_CHECK_LAUNCH("sim_finish_kernel");
+    return 0;
+  }
   float* a = workspace;
   float* b = a + (size_t)n1 * ws;
   float* gold_score = b + (size_t)n2 * ws;
@@ -465,7 +499,7 @@ extern "C" int64_t mke_sim_topk_workspace_floats(int32_t n, int32_t dim, int32_t
   if (n < 0 || dim <= 0 || chunk_rows <= 0) return -1;
   const int64_t pitch = ((int64_t)n + 3) & ~3ll;
   const int64_t rows = chunk_rows < n ? chunk_rows : n;
-  return (int64_t)n * sim_ws(dim) + rows * pitch + 8;
+  return 2 * (int64_t)n * sim_ws(dim) + rows * pitch + 8;  // prepared rows (TF32 part + remainder), `rows` rows of sims
 }
 
 extern "C" int mke_sim_topk(const float* emb, const int32_t* idx_or_null, int32_t n, int32_t stride, int32_t dim,
@@ -482,16 +516,28 @@ extern "C" int mke_sim_topk(const float* emb, const int32_t* idx_or_null, int32_
   cudaStream_t stream = (cudaStream_t)stream_;
   const int ws = sim_ws(dim);
   const size_t pitch = ((size_t)n + 3) & ~(size_t)3;
-  const int64_t left = workspace_floats - (int64_t)n * ws;
+  const bool tc = sim_use_tc();
+  const int64_t left = workspace_floats - (tc ? 2 : 1) * (int64_t)n * ws;
   MKE_CHECK_ARG(left >= (int64_t)pitch, "workspace of %lld floats holds no row of sims (see mke_sim_topk_workspace_floats)",
                 (long long)workspace_floats);
   int chunk = (int)((left / (int64_t)pitch) < n ? (left / (int64_t)pitch) : n);
   if (chunk > kSimTile) chunk -= chunk % kSimTile;  // whole tiles of A per launch
   float* a = workspace;
-  float* sims = a + (size_t)n * ws;
-  if (int rc = sim_prepare(emb, idx_or_null, n, stride, dim, normalize, a, ws, stream)) return rc;
+  float* sims = a + (tc ? 2 : 1) * (size_t)n * ws;
+  if (tc) {
+    if (int rc = sim_prepare_tc(emb, idx_or_null, n, stride, dim, normalize, a, a + (size_t)n * ws, stream)) return rc;
+  } else {
+    if (int rc = sim_prepare(emb, idx_or_null, n, stride, dim, normalize, a, ws, stream)) return rc;
+  }
   for (int r0 = 0; r0 < n; r0 += chunk) {
     const int rows = r0 + chunk < n ? chunk : n - r0;
+    if (tc) {
+      if (int rc = sim_store_tc(a, a + (size_t)n * ws, n, ws, r0, rows, sims, pitch, stream)) return rc;
+      row_topk_kernel<<<rows, kTopkThreads, 0, stream>>>(sims, pitch, n, k, id_list_or_null, id_base, neighbours_out,
+                                                          out_rows_or_null, r0);
+      MKE_CHECK_LAUNCH("row_topk_kernel");
+      continue;
+    }
     SimParams p{};
     p.a = a;
     p.n1 = n;

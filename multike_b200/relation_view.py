@@ -159,8 +159,7 @@ class RelationView:
         if self._step_loss.numel() < n_steps:
             self._step_loss = torch.zeros(n_steps, dtype=torch.float64, device=self.device)
             self._view.step_loss = self._step_loss.data_ptr()
-        self._step_loss[:n_steps].zero_()
-        v = self._view
+        v = self._view   # (step_loss[:n_steps] is zeroed by the library call)
         if host_fed:
             if self._host_triples is None:
                 self.use_host_triples()

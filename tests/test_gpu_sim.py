@@ -23,6 +23,17 @@ def S():
     return similarity
 
 
+@pytest.fixture(autouse=True, params=["tcgen05", "fma"])
+def impl(request):
+    """every test runs on both implementations: the tensor-core tiles (default, csrc/mke_sim_tc.cu) and the fp32
+    FMA tiles kept as the baseline (csrc/mke_sim.cu)"""
+    from multike_b200 import _cabi
+    lib = _cabi.load()
+    prev = lib.mke_sim_use_tensor_cores(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    lib.mke_sim_use_tensor_cores(prev)
+
+
 @pytest.fixture(scope="module")
 def ref(golden):
     return golden("ref_sim.npz")

@@ -37,6 +37,11 @@ def main():
         return
     gen = torch.Generator(device="cuda").manual_seed(0)
     out = {}
+    from multike_b200 import _cabi
+    lib = _cabi.load()
+    if "--fma" in sys.argv:  # the fp32 FMA tiles (baseline) instead of the tensor-core tiles
+        lib.mke_sim_use_tensor_cores(0)
+    out["impl"] = "tcgen05_3xtf32" if lib.mke_sim_use_tensor_cores(-1) else "fp32_fma"
     for name, n1, n2 in (("valid_10k_x_70k", 10000, 70000), ("test_60k_x_60k", 60000, 60000)):
         a = torch.randn(n1, d, device="cuda", generator=gen)
         b = torch.randn(n2, d, device="cuda", generator=gen)
