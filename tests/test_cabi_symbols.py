@@ -55,7 +55,7 @@ def test_similarity_and_ownership_entry_points_validate_on_the_host():
     # both row sets as TF32 part + remainder, the gathered gold rows likewise, gold scores, arg-max keys
     assert lib.mke_sim_rank_workspace_floats(10000, 70000, 75) == 80 * (4 * 10000 + 2 * 70000) + 10000 + 2 * 10000 + 8
     assert lib.mke_sim_rank_workspace_floats(-1, 5, 75) == -1
-    assert lib.mke_sim_topk_workspace_floats(100000, 75, 8192) == 100000 * 80 + 8192 * 100000 + 8
+    assert lib.mke_sim_topk_workspace_floats(100000, 75, 8192) == 2 * 100000 * 80 + 8192 * 100000 + 8
     assert lib.mke_sim_rank(None, None, 5, None, None, 5, 80, 75, 1, None, None, None, None, None) == _cabi.MKE_EINVAL
     assert b"null pointer" in lib.mke_last_error()
     assert lib.mke_sim_rank(None, None, 0, None, None, 5, 80, 75, 1, None, None, None, None, None) == 0  # no rows: no-op
