@@ -506,6 +506,24 @@ int mke_ipc_open(const unsigned char handle[64], void** ptr);    /* cudaIpcOpenM
 int mke_ipc_close(void* ptr);
 
 /* ------------------------------------------------------------------------------------------
+ * Row staging for row-sharded tables (BASELINE configs[3]: the attribute-view CNN MultiKE_model.py:134-151, the
+ * cross-KG graphs :158-221, ITC :225-239 and the SSL mapping :241-261 on sharded entity tables).  Those graphs
+ * run unchanged on a plain local table that holds the rows of their batch:
+ *   mke_table_stage_rows   staged.var[i] = raw row ids[i] of `table` (read through the owner's peer mapping when
+ *                          table->n_shards > 1), staged.grad[i] = 0, for i < n <= staged->rows; ids may repeat;
+ *   mke_table_commit_grads table.grad[ids[i]] += staged.grad[i] for the ids THIS rank owns (all ids of a plain
+ *                          table), touched flags set; follow with mke_rows_apply_adagrad on `table`;
+ *   mke_peer_barrier       rank `rank` stores seq into slot `rank` of every rank's flag array (flags[k]: >= 8
+ *                          uint32 of peer-mapped memory of rank k, zero-initialised) and waits until every slot of
+ *                          its own array has reached seq; seq must grow by one per call on every rank.
+ * ---------------------------------------------------------------------------------------- */
+int mke_table_stage_rows(const mke_table_t* table, const int32_t* ids, int32_t n, const mke_table_t* staged,
+                         mke_stream_t stream);
+int mke_table_commit_grads(const mke_table_t* table, const int32_t* ids, int32_t n, const mke_table_t* staged,
+                           mke_stream_t stream);
+int mke_peer_barrier(void* const* flags, int32_t world, int32_t rank, uint32_t seq, mke_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Similarity search on dense fp32 rows (evaluation and truncated-epsilon neighbours).
  * Inputs are row-major [*, stride] device arrays of which the first `dim` columns count
  * (dim <= 128); idx_or_null gathers rows (NULL => rows 0..n-1 in order); normalize != 0 divides

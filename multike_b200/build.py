@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmultike_b200.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
-SOURCES = ["mke_rel.cu", "mke_rel_q8.cu", "mke_rel_q8p.cu", "mke_rel_persist.cu", "mke_triple.cu", "mke_apply.cu", "mke_sampler.cu", "mke_epoch.cu", "mke_sharded.cu", "mke_gemm.cu", "mke_dense.cu", "mke_align.cu", "mke_space.cu", "mke_cnn.cu", "mke_sim.cu", "mke_sim_tc.cu", "mke_util.cu"]
+SOURCES = ["mke_rel.cu", "mke_rel_q8.cu", "mke_rel_q8p.cu", "mke_rel_persist.cu", "mke_triple.cu", "mke_apply.cu", "mke_sampler.cu", "mke_epoch.cu", "mke_sharded.cu", "mke_gemm.cu", "mke_dense.cu", "mke_align.cu", "mke_space.cu", "mke_cnn.cu", "mke_sim.cu", "mke_sim_tc.cu", "mke_stage.cu", "mke_util.cu"]
 HEADERS = ["mke_common.cuh", "mke_rel.cuh", "mke_sampler.cuh", "mke_q8.cuh", "mke_rel_q8p.cuh", "mke_apply.cuh", "mke_rel_persist.cuh", "mke_umma.cuh", os.path.join(ROOT, "include", "multike_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -101,14 +101,17 @@ class MultiKE:
             len(value_vectors), dim, False, dev, init=np.asarray(value_vectors, np.float32), trainable=False)
         self.name_embeds = None if name_vectors is None else T.EmbeddingTable(
             len(name_vectors), dim, False, dev, init=np.asarray(name_vectors, np.float32), trainable=False)
-        self.av_ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["av_ent_embeds"], flags=True,
-                                              grad_replicas=1)
+        self.av_ent_embeds = self._entity_table("av_ent_embeds")
         # False important! (MultiKE_model.py:96-97)
         self.attr_embeds = T.EmbeddingTable(max(n_attr, 1), dim, False, dev, init=self._init["attr_embeds"])
-        self.ent_embeds = T.EmbeddingTable(n_ent, dim, True, dev, init=self._init["ent_embeds"], flags=True,
-                                           grad_replicas=1)
+        self.ent_embeds = self._entity_table("ent_embeds")
         self.rv_ent_embeds = None  # created with the relation-view graph (they own the triple lists)
         self.rel_embeds = None
+
+    def _entity_table(self, name):
+        """a trainable [entities, dim] table read through l2_normalize(., 1) (the multi-GPU model shards these)"""
+        return T.EmbeddingTable(self.kgs.entities_num, self.args.dim, True, self.device, init=self._init[name], flags=True,
+                                grad_replicas=1)
 
     # --- view-specific graphs ---------------------------------------------------------------
     def _define_name_view_graph(self):
@@ -262,6 +265,21 @@ class MultiKE:
         self.eye_mat = torch.eye(dim, device=self.device)
         self._sm_slot = "shared_comb"
 
+    def _space_step(self, idx, ws, total, lr, ow):
+        """one session.run of the space-mapping graph: forward + backward of the three mapping losses in three
+        launches (csrc/mke_space.cu): gradient rows of the shared table and the three mapping gradients; only
+        `shared*` variables train (:257)"""
+        lib = _cabi.load()
+        F_tab = self.ent_embeds
+        _cabi.check(lib.mke_space_mapping_fwd_bwd(
+            F_tab.c, self.name_embeds.c, self._rv.ent.c, self.av_ent_embeds.c, idx.data_ptr(), idx.numel(),
+            self._maps.data_ptr(), self._maps_grad.data_ptr(), float(ow), 0.0001, ws.data_ptr(), total.data_ptr(),
+            _cabi.current_stream()))
+        F_tab.apply_adagrad(self._sm_slot, lr)
+        _cabi.check(lib.mke_dense_apply_adagrad(self._maps.data_ptr(), self._maps_grad.data_ptr(),
+                                                self._maps_acc.data_ptr(), self._maps.numel(), float(lr),
+                                                _cabi.current_stream()))
+
     def train_shared_space_mapping_1epo(self, epoch, entities):
         start = time.time()
         lib = _cabi.load()
@@ -270,27 +288,24 @@ class MultiKE:
         steps = int(math.ceil(n / self.args.entity_batch_size))
         batch_size = self.args.entity_batch_size if steps > 1 else n
         lr, ow = self.args.learning_rate, self.args.orthogonal_weight
-        F_tab = self.ent_embeds
         total = torch.zeros(1, dtype=torch.float64, device=self.device)
-        dim = F_tab.dim
+        dim = self.ent_embeds.dim
         ws = torch.empty(int(lib.mke_space_mapping_workspace_floats(batch_size, dim)), dtype=torch.float32,
                          device=self.device)
         for _ in range(steps):
             idx = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()  # random.sample: distinct ids
-            # forward + backward of the three mapping losses in three launches (csrc/mke_space.cu): gradient rows
-            # of the shared table and the three mapping gradients; only `shared*` variables train (:257)
-            _cabi.check(lib.mke_space_mapping_fwd_bwd(
-                F_tab.c, self.name_embeds.c, self._rv.ent.c, self.av_ent_embeds.c, idx.data_ptr(), idx.numel(),
-                self._maps.data_ptr(), self._maps_grad.data_ptr(), float(ow), 0.0001, ws.data_ptr(), total.data_ptr(),
-                _cabi.current_stream()))
-            F_tab.apply_adagrad(self._sm_slot, lr)
-            _cabi.check(lib.mke_dense_apply_adagrad(self._maps.data_ptr(), self._maps_grad.data_ptr(),
-                                                    self._maps_acc.data_ptr(), self._maps.numel(), float(lr),
-                                                    _cabi.current_stream()))
+            self._space_step(idx, ws, total, lr, ow)
         epoch_loss = float(total) / max(steps * batch_size, 1)
         print('epoch {} of shared space learning, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss,
                                                                                            time.time() - start))
         return epoch_loss
+
+    def _align_step(self, pick, acc, lr, cvw):
+        """one session.run of the common-space graph (:225-239)"""
+        T.align_fwd_bwd(self.ent_embeds, self.name_embeds, self._rv.ent, self.av_ent_embeds, pick, acc,
+                        name_weight=self.args.cv_name_weight, scale=cvw)
+        for t in (self.ent_embeds, self._rv.ent, self.av_ent_embeds):
+            t.apply_adagrad(self._cn_slot, lr)
 
     def train_common_space_learning_1epo(self, epoch, entities):
         """MultiKE_model.py:458-473"""
@@ -301,14 +316,10 @@ class MultiKE:
         batch_size = self.args.entity_batch_size if steps > 1 else n
         acc = T.new_loss_accumulator(self.device)
         lr, cvw = self.args.ITC_learning_rate, float(self.args.cv_weight)
-        tabs = (self.ent_embeds, self._rv.ent, self.av_ent_embeds)
         trained = 0
         for _ in range(steps):
             pick = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()  # random.sample
-            T.align_fwd_bwd(self.ent_embeds, self.name_embeds, self._rv.ent, self.av_ent_embeds, pick, acc,
-                            name_weight=self.args.cv_name_weight, scale=cvw)
-            for t in tabs:
-                t.apply_adagrad(self._cn_slot, lr)
+            self._align_step(pick, acc, lr, cvw)
             trained += batch_size
         # the fetched cross_name_loss is the un-weighted sum (the optimizer minimises cv_weight * loss)
         epoch_loss = float(acc.item()) / (cvw if cvw != 0 else 1.0) / max(trained, 1)
@@ -358,6 +369,14 @@ class MultiKE:
         print('epoch {} of rel. view, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss, end - start))
         return epoch_loss
 
+    def _positives_only_step(self, pos, w, acc, slot):
+        rv = self._rv
+        T.rel_step_structured(rv.ent, rv.rel, pos, None, None, 0, acc, w=w, pos_scale=2.0, variant=rv.variant)
+        T.apply_adagrad_pair(rv.ent, rv.ent.adagrad_slot(slot), rv.lr, rv.rel, rv.rel.adagrad_slot(slot), rv.lr)
+
+    def _end_of_epoch_sync(self):
+        """hook of the multi-GPU model (multike_b200/sharded_model.py); nothing to do on one GPU"""
+
     def _positives_only_epoch(self, sup_triples, slot, weighted):
         """MultiKE_model.py:349-369 / 393-414: `steps` batches of random.sample(sup_triples, B),
         loss = 2 * [weighted] logistic loss without negatives, Adagrad slots of this graph."""
@@ -372,10 +391,7 @@ class MultiKE:
         trained = 0
         for _ in range(steps):
             pick = torch.randperm(n, device=rv.device)[:batch_size]  # random.sample: without replacement
-            T.rel_step_structured(rv.ent, rv.rel, pos_d[pick].contiguous(), None, None, 0, acc,
-                                  w=None if w_d is None else w_d[pick].contiguous(), pos_scale=2.0,
-                                  variant=rv.variant)
-            T.apply_adagrad_pair(rv.ent, rv.ent.adagrad_slot(slot), rv.lr, rv.rel, rv.rel.adagrad_slot(slot), rv.lr)
+            self._positives_only_step(pos_d[pick].contiguous(), None if w_d is None else w_d[pick].contiguous(), acc, slot)
             trained += batch_size
         return float(acc.item()) / max(trained, 1)
 

@@ -126,6 +126,7 @@ class _Schedule:
         m.train_cross_kg_entity_inference_attribute_view_1epo(i, self.ckge_attribute)
         if soft:
             m.train_cross_kg_attribute_inference_1epo(i, self.ckgp_attribute)
+        m._end_of_epoch_sync()
 
     def refresh_neighbours(self, m, i):
         """truncated-epsilon candidates every truncated_freq epochs (MultiKE_CSL.py:89-103)"""
@@ -215,6 +216,7 @@ class MultiKE_Late(_Driver):
             plan.refresh_neighbours(self, i)
         for i in range(1, self.args.shared_learning_max_epoch + 1):
             self.train_shared_space_mapping_1epo(i, plan.entity_list)
+            self._end_of_epoch_sync()
             if self._due(i):
                 valid(self, embed_choice='final')
         self.save()

@@ -318,6 +318,11 @@ class ShardedRelationView:
     def triple_steps(self):
         return int(math.ceil((self.n1 + self.n2) / self.global_batch))
 
+    def set_neighbours(self, nb1, nb2):
+        """truncated-eps candidate lists (base/batch.py:119-150, MultiKE_CSL.py:89-99): the same table on every rank"""
+        self.kg1.set_neighbours(nb1, self.device)
+        self.kg2.set_neighbours(nb2, self.device)
+
     def plan(self, step_in_epoch):
         """(positives of kg1, of kg2, index_base, own_lo, own_hi, positives this rank answers for) of one global
         step for this rank -- what csrc/mke_sharded.cu::make_plan computes; kept for the CPU tests"""

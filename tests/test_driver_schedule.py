@@ -30,6 +30,9 @@ class Recorder:
     def save(self):
         self.log.append("save")
 
+    def _end_of_epoch_sync(self):   # hook of the multi-GPU model: not part of the reference's schedule
+        pass
+
     def _due(self, i):
         return drivers._Driver._due(self, i)
 

@@ -23,3 +23,17 @@ def test_sharded_relation_view_equals_single_gpu(world, by_kg):
     out = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
                          env=dict(os.environ, MKE_BY_KG=by_kg, MKE_SAME_GPU="1" if same_gpu else "0"))
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-4000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_multiview_drivers_equal_single_gpu(world):
+    """BASELINE configs[3] in small: run_SSL.py's and run_ITC.py's schedules on row-sharded entity tables
+    (multike_b200/sharded_model.py) print the single-GPU drivers' losses and evaluation lines"""
+    same_gpu = torch.cuda.device_count() < world
+    if same_gpu and world > 2:
+        pytest.skip("needs %d GPUs (the shared-GPU mode is run at world 2 only)" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29530 + world), os.path.join(ROOT, "tests", "multi_gpu_model_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200,
+                         env=dict(os.environ, MKE_SAME_GPU="1" if same_gpu else "0", PYTHONHASHSEED="0"))
+    assert "MULTI_GPU_MODEL_CHECK PASS" in out.stdout, out.stdout[-6000:]
