@@ -533,8 +533,10 @@ int mke_peer_barrier(void* const* flags, int32_t world, int32_t rank, uint32_t s
  * ------------------------------------------------------------------------------------------ */
 
 /* Which implementation mke_sim_rank / mke_sim_topk run: 1 (default) = tcgen05 tiles at fp32-equivalent precision
- * (3xTF32 split, csrc/mke_sim_tc.cu), 0 = the fp32 FMA tiles of csrc/mke_sim.cu (the measured baseline).  on < 0 only
- * queries.  Returns the previous setting.  The same tie rules hold for both (equal rows give bit-equal sims). */
+ * (3xTF32 split, csrc/mke_sim_tc.cu; mke_sim_topk then never writes the similarity matrix: sampled per-row threshold,
+ * candidate lists from the tile epilogue, exact select per row, exact path for the rare row whose list came out short),
+ * 2 = the same tiles but mke_sim_topk materialises rows of sims and selects from them, 0 = the fp32 FMA tiles of
+ * csrc/mke_sim.cu (the measured baseline).  on < 0 only queries.  Returns the previous setting.  The same tie rules hold for both (equal rows give bit-equal sims). */
 int mke_sim_use_tensor_cores(int32_t on);
 
 /* floats of workspace mke_sim_rank needs (prepared copies of both row sets + per-row scratch) */

@@ -423,6 +423,17 @@ int sim_store_tc(const float* hi, const float* lo, int n, int ws, int row_base, 
 int sim_prepare_tc(const float* src, const int32_t* idx, int n, int stride, int dim, int normalize, float* hi, float* lo,
                    cudaStream_t stream);
 static int g_sim_tc = -1;  // -1: not decided yet (MKE_SIM_TC, default on)
+int sim_topk_fused_tc(const float* hi, const float* lo, int n, int ws, int k, const int32_t* id_list, int id_base,
+                      const int32_t* out_rows, float* work, int64_t work_floats, int32_t* out, cudaStream_t stream);
+bool sim_topk_fused_applies(int n, int k);
+// exact top-k of `rows` rows of sims (row r -> output row out_rows[r]); used by the fall-back of the fused search
+int sim_topk_rows_exact(const float* sims, size_t pitch, int n, int k, const int32_t* id_list, int id_base, int32_t* out,
+                        const int32_t* out_rows, int rows, cudaStream_t stream) {
+  row_topk_kernel<<<rows, kTopkThreads, 0, stream>>>(sims, pitch, n, k, id_list, id_base, out, out_rows, 0);
+  MKE_CHECK_LAUNCH("row_topk_kernel");
+  return 0;
+}
+static int g_sim_fused = -1;  // MKE_SIM_FUSED=0: always materialise the rows of sims (the exact path)
 static bool sim_use_tc() {
   if (g_sim_tc < 0) g_sim_tc = getenv("MKE_SIM_TC") ? (atoi(getenv("MKE_SIM_TC")) != 0) : 1;
   return g_sim_tc != 0;
@@ -433,8 +444,12 @@ static bool sim_use_tc() {
 using namespace mke;
 
 extern "C" int mke_sim_use_tensor_cores(int32_t on) {
-  const int prev = sim_use_tc() ? 1 : 0;
-  if (on >= 0) g_sim_tc = on != 0;
+  if (g_sim_fused < 0) g_sim_fused = getenv("MKE_SIM_FUSED") ? (atoi(getenv("MKE_SIM_FUSED")) != 0) : 1;
+  const int prev = sim_use_tc() ? (g_sim_fused ? 1 : 2) : 0;
+  if (on >= 0) {
+    g_sim_tc = on != 0;
+    g_sim_fused = on != 2;
+  }
   return prev;
 }
 
@@ -526,6 +541,12 @@ extern "C" int mke_sim_topk(const float* emb, const int32_t* idx_or_null, int32_
   float* sims = a + (tc ? 2 : 1) * (size_t)n * ws;
   if (tc) {
     if (int rc = sim_prepare_tc(emb, idx_or_null, n, stride, dim, normalize, a, a + (size_t)n * ws, stream)) return rc;
+    if (g_sim_fused < 0) g_sim_fused = getenv("MKE_SIM_FUSED") ? (atoi(getenv("MKE_SIM_FUSED")) != 0) : 1;
+    if (g_sim_fused && sim_topk_fused_applies(n, k)) {
+      const int rc = sim_topk_fused_tc(a, a + (size_t)n * ws, n, ws, k, id_list_or_null, id_base, out_rows_or_null, sims,
+                                       workspace_floats - 2 * (int64_t)n * ws, neighbours_out, stream);
+      if (rc <= 0) return rc;  // 1: the workspace is too small for it
+    }
   } else {
     if (int rc = sim_prepare(emb, idx_or_null, n, stride, dim, normalize, a, ws, stream)) return rc;
   }

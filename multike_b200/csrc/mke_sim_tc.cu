@@ -29,7 +29,7 @@ constexpr int kTcTile = 128;
 constexpr int kTcBoxBytes = kTcTile * 32 * 4;  // one operand box: 128 rows x one 128-byte swizzle row
 constexpr int kTcSmemBudget = 224 * 1024;     // A (nkb x 2 boxes) + ring (stages x 2 boxes)
 
-enum { kTcRank = 0, kTcStore = 1, kTcGold = 2 };
+enum { kTcRank = 0, kTcStore = 1, kTcGold = 2, kTcFilter = 3 };
 
 struct SimTcParams {
   int n1, n2;        // rows of A / of B
@@ -45,6 +45,11 @@ struct SimTcParams {
   unsigned long long* best;
   float* out;
   size_t out_pitch;
+  // FILTER: columns whose sim reaches the row's threshold are appended to the row's candidate list
+  const float* tau;     // [rows]
+  uint32_t* cand_cnt;   // [rows] (may exceed cap: the row then takes the exact path)
+  uint2* cand;          // [rows][cap] (column, sim bits)
+  int cap;
 };
 
 __device__ __forceinline__ uint32_t tc_ord_key(float f) {
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     int cnt = 0, bi = 0x7fffffff;
     float bs = __int_as_float(0xff800000);
     float diag = 0.f;
+    const float tau_r = (MODE == kTcFilter && row_ok) ? __ldg(p.tau + (r - p.row_base)) : 0.f;
     float* const orow = MODE == kTcStore ? p.out + (size_t)(row_ok ? r - p.row_base : 0) * p.out_pitch : nullptr;
     int t = 0;
 #pragma unroll 1
@@ -229,6 +235,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 w.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
                 w.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
                 __stcs(reinterpret_cast<float4*>(orow + col), w);
+              }
+            }
+          }
+        } else if (MODE == kTcFilter) {
+          if (row_ok) {
+            uint32_t hit = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+              v[j] = __float_as_uint(s);
+              hit |= (col0 + j < p.n2 && s >= tau_r) ? (1u << j) : 0u;
+            }
+            if (hit != 0u) {
+              const int c = __popc(hit);
+              const uint32_t pos = atomicAdd(p.cand_cnt + (r - p.row_base), (uint32_t)c);
+              if (pos + (uint32_t)c <= (uint32_t)p.cap) {
+                uint2* dst = p.cand + (size_t)(r - p.row_base) * p.cap + pos;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if ((hit >> j) & 1u) *dst++ = make_uint2((uint32_t)(col0 + j), v[j]);
               }
             }
           }
@@ -338,7 +364,7 @@ static int launch_sim_tc(const float* a_hi, const float* a_lo, const float* b_hi
   if (p.stages > 6) p.stages = 6;
   const int smem = (p.nkb + p.stages) * 2 * kTcBoxBytes + 1024 + 256;
   auto kern = sim_tc_kernel<MODE>;
-  static int configured[3] = {0, 0, 0};
+  static int configured[4] = {0, 0, 0, 0};
   if (configured[MODE] < smem) {
     if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
       return cuda_fail(e, "cudaFuncSetAttribute(sim_tc_kernel)");
@@ -349,6 +375,325 @@ static int launch_sim_tc(const float* a_hi, const float* a_lo, const float* b_hi
   p.splits = MODE == kTcGold ? 1 : sim_tc_splits(row_blocks, ntiles);
   kern<<<row_blocks * p.splits, kTcThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   MKE_CHECK_LAUNCH("sim_tc_kernel");
+  return 0;
+}
+
+// ---- truncated-epsilon neighbour lists without the similarity matrix ------------------------------------------------
+// find_neighbours (base/batch.py:141-150) keeps the k = 2 % most similar columns of each of 100 000 rows.  Instead of
+// writing 40 GB of sims and selecting from them: (1) sims of every row with a SAMPLE of 4 096 columns (STORE tiles, 4 % of
+// the work) give a per-row threshold that, with 3.4 sigma of margin, at least k columns of the full row reach; (2) the
+// FILTER tiles append the (column, sim) pairs that reach it to a candidate list per row (about 1.3 k of them); (3) one
+// block per row selects the exact top k of its candidates (radix select in shared memory) and emits them in ascending
+// column order through a bitmap.  A row whose list came out short or overflowed is redone on the exact path.
+
+__device__ __forceinline__ float tc_key_to_float(uint32_t key) {
+  return __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
+}
+
+// key of the kth largest (kth >= 1) of n_keys keys in shared memory, and how many keys equal to it belong to the top kth
+// (block of 256 threads; hist: 2048 words of shared memory)
+__device__ void block_kth_key(const uint32_t* keys, int n_keys, unsigned kth, unsigned* hist, unsigned* s_pair, uint32_t& T,
+                              unsigned& need_eq) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t prefix = 0u, mask = 0u;
+  unsigned remaining = kth;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+    const int nb = pass < 2 ? 2048 : 1024;
+    for (int b = tid; b < nb; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n_keys; i += blockDim.x) {
+      const uint32_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & (unsigned)(nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {  // lane l owns bins [l per, (l + 1) per); suffix sums from the top bin down
+      const int per = nb / 32;
+      unsigned mine = 0u;
+      for (int b = 0; b < per; ++b) mine += hist[lane * per + b];
+      unsigned above = 0u;
+      for (int l = 31; l > 0; --l) {
+        const unsigned v = __shfl_sync(0xffffffffu, mine, l);
+        if (l > lane) above += v;
+      }
+      if (above < remaining && remaining <= above + mine) {
+        unsigned acc = above;
+        for (int b = per - 1; b >= 0; --b) {
+          const unsigned h = hist[lane * per + b];
+          if (acc + h >= remaining) {
+            s_pair[0] = (unsigned)(lane * per + b);
+            s_pair[1] = acc;
+            break;
+          }
+          acc += h;
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= s_pair[0] << shift;
+    mask |= (unsigned)(nb - 1) << shift;
+    remaining -= s_pair[1];
+    __syncthreads();
+  }
+  T = prefix;
+  need_eq = remaining;
+}
+
+constexpr int kTcSample = 4096;     // sampled columns
+constexpr int kSelThreads = 256;
+
+// tau[row] = the m-th largest of the row's sims with the sampled columns
+__global__ void __launch_bounds__(kSelThreads) sim_tc_threshold_kernel(const float* __restrict__ ssims, int S, unsigned m,
+                                                                        float* __restrict__ tau, uint32_t* __restrict__ cnt) {
+  __shared__ uint32_t keys[kTcSample];
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned s_pair[2];
+  const float* row = ssims + (size_t)blockIdx.x * S;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) keys[i] = tc_ord_key(row[i]);
+  __syncthreads();
+  uint32_t T;
+  unsigned need;
+  block_kth_key(keys, S, m, hist, s_pair, T, need);
+  if (threadIdx.x == 0) {
+    tau[blockIdx.x] = tc_key_to_float(T);
+    cnt[blockIdx.x] = 0u;
+  }
+}
+
+__global__ void sim_tc_sample_rows_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int n, int ws, int S,
+                                          float* __restrict__ s_hi, float* __restrict__ s_lo) {
+  const int j = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= S) return;
+  const size_t src = (size_t)(((long long)j * n) / S) * ws;
+  for (int c = lane; c < ws; c += 32) {
+    s_hi[(size_t)j * ws + c] = hi[src + c];
+    s_lo[(size_t)j * ws + c] = lo[src + c];
+  }
+}
+
+__global__ void sim_tc_gather_rows_kernel(const float* __restrict__ hi, const float* __restrict__ lo, const int32_t* __restrict__ rows,
+                                          int row_base, int nf, int ws, float* __restrict__ g_hi, float* __restrict__ g_lo,
+                                          const int32_t* __restrict__ out_rows, int32_t* __restrict__ mapped) {
+  const int j = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= nf) return;
+  const int r = row_base + rows[j];
+  for (int c = lane; c < ws; c += 32) {
+    g_hi[(size_t)j * ws + c] = hi[(size_t)r * ws + c];
+    g_lo[(size_t)j * ws + c] = lo[(size_t)r * ws + c];
+  }
+  if (lane == 0) mapped[j] = out_rows ? out_rows[r] : r;
+}
+
+struct SelectParams {
+  const uint2* cand;
+  const uint32_t* cnt;
+  int cap, k, n, row_base;
+  const int32_t* id_list;
+  int id_base;
+  int32_t* out;
+  const int32_t* out_rows;
+  int32_t* fb_list;     // rows (relative to row_base) that take the exact path
+  uint32_t* fb_count;
+};
+
+// exclusive prefix sum over the block's threads
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_warp, unsigned& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned base = 0u, tot = 0u;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    if (w < warp) base += s_warp[w];
+    tot += s_warp[w];
+  }
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kSelThreads) sim_tc_select_kernel(const SelectParams p) {
+  extern __shared__ uint32_t s_sel[];
+  uint32_t* keys = s_sel;                 // [cap]
+  uint32_t* cols = keys + p.cap;          // [cap]
+  const int words = (p.n + 31) >> 5;
+  uint32_t* gt = cols + p.cap;            // [words]
+  uint32_t* eq = gt + words;              // [words]
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned s_pair[2];
+  __shared__ unsigned s_warp[kSelThreads / 32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const uint32_t c = p.cnt[row];
+  if (c < (uint32_t)p.k || c > (uint32_t)p.cap) {  // short (threshold too high) or overflowed: the exact path redoes it
+    if (tid == 0) p.fb_list[atomicAdd(p.fb_count, 1u)] = row;
+    return;
+  }
+  const uint2* cand = p.cand + (size_t)row * p.cap;
+  for (int i = tid; i < (int)c; i += blockDim.x) {
+    const uint2 e = cand[i];
+    cols[i] = e.x;
+    keys[i] = tc_ord_key(__uint_as_float(e.y));
+  }
+  for (int w = tid; w < words; w += blockDim.x) {
+    gt[w] = 0u;
+    eq[w] = 0u;
+  }
+  __syncthreads();
+  uint32_t T;
+  unsigned need_eq;
+  block_kth_key(keys, (int)c, (unsigned)p.k, hist, s_pair, T, need_eq);
+  for (int i = tid; i < (int)c; i += blockDim.x) {
+    const uint32_t key = keys[i], col = cols[i];
+    if (key > T)
+      atomicOr(&gt[col >> 5], 1u << (col & 31));
+    else if (key == T)
+      atomicOr(&eq[col >> 5], 1u << (col & 31));
+  }
+  __syncthreads();
+  // ties at the k-th value: the first need_eq of them in ascending column order (the stable rule of the exact path)
+  const int per = (words + blockDim.x - 1) / blockDim.x;
+  const int w0 = tid * per < words ? tid * per : words, w1 = (tid + 1) * per < words ? (tid + 1) * per : words;
+  unsigned mine = 0u, total;
+  for (int w = w0; w < w1; ++w) mine += __popc(eq[w]);
+  unsigned base = block_excl_scan(mine, s_warp, total);
+  for (int w = w0; w < w1; ++w) {
+    uint32_t word = eq[w];
+    const unsigned pc = __popc(word);
+    if (base >= need_eq) {
+      word = 0u;
+    } else if (base + pc > need_eq) {
+      unsigned keep = need_eq - base;
+      uint32_t kept = 0u;
+      while (keep-- > 0u) {
+        const uint32_t low = word & (0u - word);
+        kept |= low;
+        word ^= low;
+      }
+      word = kept;
+    }
+    base += pc;
+    gt[w] |= word;
+  }
+  __syncthreads();
+  mine = 0u;
+  for (int w = w0; w < w1; ++w) mine += __popc(gt[w]);
+  unsigned pos = block_excl_scan(mine, s_warp, total);
+  const int orow = p.out_rows ? __ldg(p.out_rows + p.row_base + row) : p.row_base + row;
+  int32_t* __restrict__ o = p.out + (size_t)orow * p.k;
+  for (int w = w0; w < w1; ++w) {
+    uint32_t word = gt[w];
+    while (word != 0u) {
+      const int col = (w << 5) + __ffs(word) - 1;
+      o[pos++] = p.id_list ? __ldg(p.id_list + col) : p.id_base + col;
+      word &= word - 1u;
+    }
+  }
+}
+
+// exact-path pieces of mke_sim.cu the fall-back uses
+int sim_topk_rows_exact(const float* sims, size_t pitch, int n, int k, const int32_t* id_list, int id_base, int32_t* out,
+                        const int32_t* out_rows, int rows, cudaStream_t stream);
+
+// floats of workspace the fused search needs beyond the prepared rows: fixed part and per fused row
+static void topk_fused_layout(int n, int ws, int k, size_t pitch, size_t& fixed, size_t& per_row, int& cap, unsigned& m) {
+  cap = (int)(((long long)(2.2 * k) + 63) & ~63ll);
+  m = (unsigned)((1.3 * (double)k * kTcSample) / (double)n) + 8u;
+  fixed = (size_t)128 * pitch + 2 * (size_t)128 * ws + 2 * (size_t)kTcSample * ws + 256;
+  per_row = (size_t)kTcSample + 2 * (size_t)cap + 4;
+}
+
+bool sim_topk_fused_applies(int n, int k) {
+  return n >= 4 * kTcSample && (long long)k * 8 <= n && n <= 262144 && k >= 64;
+}
+
+// hi / lo: prepared rows [n, ws]; work: workspace after them (work_floats floats).  Returns 1 when the workspace is too
+// small for the fused search (the caller runs the exact one).
+int sim_topk_fused_tc(const float* hi, const float* lo, int n, int ws, int k, const int32_t* id_list, int id_base,
+                      const int32_t* out_rows, float* work, int64_t work_floats, int32_t* out, cudaStream_t stream) {
+  const size_t pitch = ((size_t)n + 3) & ~(size_t)3;
+  size_t fixed, per_row;
+  int cap;
+  unsigned m;
+  topk_fused_layout(n, ws, k, pitch, fixed, per_row, cap, m);
+  if (work_floats < (int64_t)(fixed + 128 * per_row)) return 1;
+  long long rf = (long long)((size_t)work_floats - fixed) / (long long)per_row;
+  if (rf > n) rf = n;
+  if (rf > kTcTile) rf -= rf % kTcTile;
+  float* ex_sims = work;                                  // [128][pitch]   exact path of the fall-back rows
+  float* g_hi = ex_sims + (size_t)128 * pitch;            // [128][ws] x 2  their prepared rows
+  float* g_lo = g_hi + (size_t)128 * ws;
+  float* s_hi = g_lo + (size_t)128 * ws;                  // [S][ws] x 2    the sampled columns
+  float* s_lo = s_hi + (size_t)kTcSample * ws;
+  float* chunk = s_lo + (size_t)kTcSample * ws + 64;
+  float* ssims = chunk;                                   // [rf][S]
+  float* tau = ssims + (size_t)rf * kTcSample;            // [rf]
+  uint32_t* cnt = (uint32_t*)(tau + rf);                  // [rf]
+  int32_t* fb_list = (int32_t*)(cnt + rf);                // [rf] + count + mapped rows
+  uint32_t* fb_count = (uint32_t*)(fb_list + rf);
+  uint2* cand = (uint2*)(((uintptr_t)(fb_count + 2) + 15) & ~(uintptr_t)15);  // [rf][cap]
+  sim_tc_sample_rows_kernel<<<(kTcSample + 7) / 8, 256, 0, stream>>>(hi, lo, n, ws, kTcSample, s_hi, s_lo);
+  MKE_CHECK_LAUNCH("sim_tc_sample_rows_kernel");
+  const int words = (n + 31) >> 5;
+  const size_t sel_smem = ((size_t)2 * cap + 2 * (size_t)words) * sizeof(uint32_t);
+  static size_t sel_configured = 0;
+  if (sel_configured < sel_smem) {
+    if (cudaError_t e = cudaFuncSetAttribute(sim_tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem))
+      return cuda_fail(e, "cudaFuncSetAttribute(sim_tc_select_kernel)");
+    sel_configured = sel_smem;
+  }
+  for (int r0 = 0; r0 < n; r0 += (int)rf) {
+    const int rows = r0 + rf < n ? (int)rf : n - r0;
+    SimTcParams ps{};  // (1) sims with the sampled columns
+    ps.n1 = n;
+    ps.n2 = kTcSample;
+    ps.row_base = r0;
+    ps.rows = rows;
+    ps.out = ssims;
+    ps.out_pitch = kTcSample;
+    if (int rc = launch_sim_tc<kTcStore>(hi, lo, s_hi, s_lo, ws, ps, stream)) return rc;
+    sim_tc_threshold_kernel<<<rows, kSelThreads, 0, stream>>>(ssims, kTcSample, m, tau, cnt);
+    MKE_CHECK_LAUNCH("sim_tc_threshold_kernel");
+    if (cudaError_t e = cudaMemsetAsync(fb_count, 0, 2 * sizeof(uint32_t), stream)) return cuda_fail(e, "memset");
+    SimTcParams pf{};  // (2) all columns, candidates only
+    pf.n1 = n;
+    pf.n2 = n;
+    pf.row_base = r0;
+    pf.rows = rows;
+    pf.tau = tau;
+    pf.cand_cnt = cnt;
+    pf.cand = cand;
+    pf.cap = cap;
+    if (int rc = launch_sim_tc<kTcFilter>(hi, lo, hi, lo, ws, pf, stream)) return rc;
+    SelectParams sp{cand, cnt, cap, k, n, r0, id_list, id_base, out, out_rows, fb_list, fb_count};  // (3)
+    sim_tc_select_kernel<<<rows, kSelThreads, sel_smem, stream>>>(sp);
+    MKE_CHECK_LAUNCH("sim_tc_select_kernel");
+    uint32_t nf = 0;  // (4) rows for the exact path (expected: a few in 10 000)
+    if (cudaError_t e = cudaMemcpyAsync(&nf, fb_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) return cuda_fail(e, "D2H");
+    if (cudaError_t e = cudaStreamSynchronize(stream)) return cuda_fail(e, "sync");
+    for (uint32_t f0 = 0; f0 < nf; f0 += 128) {
+      const int cnt_f = nf - f0 < 128 ? (int)(nf - f0) : 128;
+      // the mapped output rows of this batch live in the first 128 words of the (now dead) sample-sims area
+      int32_t* mapped = (int32_t*)ssims;
+      sim_tc_gather_rows_kernel<<<(cnt_f + 7) / 8, 256, 0, stream>>>(hi, lo, fb_list + f0, r0, cnt_f, ws, g_hi, g_lo, out_rows, mapped);
+      MKE_CHECK_LAUNCH("sim_tc_gather_rows_kernel");
+      SimTcParams pe{};
+      pe.n1 = cnt_f;
+      pe.n2 = n;
+      pe.row_base = 0;
+      pe.rows = cnt_f;
+      pe.out = ex_sims;
+      pe.out_pitch = pitch;
+      if (int rc = launch_sim_tc<kTcStore>(g_hi, g_lo, hi, lo, ws, pe, stream)) return rc;
+      if (int rc = sim_topk_rows_exact(ex_sims, pitch, n, k, id_list, id_base, out, mapped, cnt_f, stream)) return rc;
+    }
+  }
   return 0;
 }
 

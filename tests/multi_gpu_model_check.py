@@ -29,7 +29,8 @@ def numbers(text):
         if "avg. loss" in line:
             out.append((line.split(",")[0], [float(NUM.findall(line.split("avg. loss:")[1])[0])]))
         elif "results: hits@" in line:
-            out.append(("hits", [float(x) for x in NUM.findall(line.split("cost")[0])]))
+            body = line.split("] = ")[1].split(", time")[0]   # "[h1 h5 h10 h50]%, mr = .., mrr = .."
+            out.append(("hits", [float(x) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", body)]))
     return out
 
 

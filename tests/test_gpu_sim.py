@@ -202,6 +202,31 @@ def test_topk_full_size_vs_float64(S):
     assert bool(chosen[torch.arange(len(pick)), pick].all())  # every entity is its own nearest neighbour
 
 
+def test_topk_fused_candidate_search_equals_the_exact_path(S, impl):
+    """the search that never writes the similarity matrix (sampled threshold -> candidate lists from the tile epilogue ->
+    select per row; rows whose list came out short redone exactly) returns the lists of the path that materialises the
+    sims, on the same tiles: bit-equal sims, so the lists are equal element by element -- with heavy ties (integer
+    rows, duplicates) and with continuous rows"""
+    if impl != "tcgen05":
+        pytest.skip("tensor-core path only")
+    from multike_b200 import _cabi
+    lib = _cabi.load()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    cases = [(torch.randn(20000, 32, device="cuda", generator=gen), 300),
+             (torch.randint(-1, 2, (17000, 24), device="cuda", generator=gen).float(), 500)]
+    cases[1][0][:4000] = cases[1][0][4000:8000]       # duplicate rows: ties at every rank
+    skew = torch.randn(16500, 75, device="cuda", generator=gen)
+    skew[:300] = skew[0] + 0.01 * torch.randn(300, 75, device="cuda", generator=gen)   # a tight cluster: rows whose
+    cases.append((skew, 250))                                                          # sampled threshold misses
+    for e, k in cases:
+        lib.mke_sim_use_tensor_cores(1)
+        fused = S.sim_topk(e, k, normalize=True, chunk_rows=2048)
+        lib.mke_sim_use_tensor_cores(2)
+        exact = S.sim_topk(e, k, normalize=True, chunk_rows=2048)
+        lib.mke_sim_use_tensor_cores(1)
+        assert torch.equal(fused, exact)
+
+
 def test_generate_neighbours_feeds_the_device_sampler(S):
     """refapi.base.batch.generate_neighbours -> NeighbourTable -> KGSampler: negatives of the
     truncated sampler come from the anchor's list (base/batch.py:93-94)."""

@@ -41,7 +41,10 @@ def main():
     lib = _cabi.load()
     if "--fma" in sys.argv:  # the fp32 FMA tiles (baseline) instead of the tensor-core tiles
         lib.mke_sim_use_tensor_cores(0)
-    out["impl"] = "tcgen05_3xtf32" if lib.mke_sim_use_tensor_cores(-1) else "fp32_fma"
+    if "--materialise" in sys.argv:  # tensor-core tiles, but the neighbour search writes rows of sims and selects from them
+        lib.mke_sim_use_tensor_cores(2)
+    out["impl"] = {0: "fp32_fma", 1: "tcgen05_3xtf32, neighbour search without the similarity matrix",
+                   2: "tcgen05_3xtf32, neighbour search from materialised sims"}[lib.mke_sim_use_tensor_cores(-1)]
     for name, n1, n2 in (("valid_10k_x_70k", 10000, 70000), ("test_60k_x_60k", 60000, 60000)):
         a = torch.randn(n1, d, device="cuda", generator=gen)
         b = torch.randn(n2, d, device="cuda", generator=gen)

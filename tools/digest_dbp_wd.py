@@ -13,8 +13,12 @@ import zipfile
 import numpy as np
 
 REF = "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
-                   "dbp_wd_100k_relation.npz")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# MKE_DATASET=DBP_YG digests DBP-YG-100K (BASELINE configs[3]) instead: written under oracle/_ref/ (git-ignored like the
+# compiled reference modules -- produced in the build container by __graft_entry__.build(), travels to the GPU box)
+DATASET = os.environ.get("MKE_DATASET", "DBP_WD")
+OUT = os.path.join(ROOT, "tests", "golden", "dbp_wd_100k_relation.npz") if DATASET == "DBP_WD" else \
+    os.path.join(ROOT, "oracle", "_ref", "%s_100k_relation.npz" % DATASET.lower())
 
 
 def main():
@@ -26,9 +30,9 @@ def main():
     from base.kgs import read_kgs_from_folder
     tmp = tempfile.mkdtemp(prefix="dbpwd_")
     with zipfile.ZipFile(os.path.join(REF, "data", "BootEA_datasets.zip")) as z:
-        members = [m for m in z.namelist() if "BootEA_DBP_WD_100K" in m]
+        members = [m for m in z.namelist() if "BootEA_%s_100K" % DATASET in m]
         z.extractall(tmp, members)
-    folder = os.path.join(tmp, "BootEA_datasets", "BootEA_DBP_WD_100K") + "/"
+    folder = os.path.join(tmp, "BootEA_datasets", "BootEA_%s_100K" % DATASET) + "/"
     kgs = read_kgs_from_folder(folder, "631/", "swapping", False)
     kg1, kg2 = kgs.kg1, kgs.kg2
     out = dict(
@@ -47,6 +51,7 @@ def main():
     assert len(kg1.local_relation_triples_set) == len(set(map(tuple, out["triples1"])) | set(map(tuple, out["sup1"])))
     for k, v in out.items():
         print(k, getattr(v, "shape", v))
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT))
 

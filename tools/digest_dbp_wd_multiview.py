@@ -21,7 +21,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-OUT = os.path.join(ROOT, "tests", "golden", "dbp_wd_100k_multiview.npz")
+DATASET = os.environ.get("MKE_DATASET", "DBP_WD")   # DBP_YG: BASELINE configs[3], written under oracle/_ref/ (see digest_dbp_wd.py)
+OUT = os.path.join(ROOT, "tests", "golden", "dbp_wd_100k_multiview.npz") if DATASET == "DBP_WD" else \
+    os.path.join(ROOT, "oracle", "_ref", "%s_100k_multiview.npz" % DATASET.lower())
 
 
 def main():
@@ -37,8 +39,8 @@ def main():
     if not folder:
         tmp = tempfile.mkdtemp(prefix="dbpwd_")
         with zipfile.ZipFile(os.path.join(REF, "data", "BootEA_datasets.zip")) as z:
-            z.extractall(tmp, [m for m in z.namelist() if "BootEA_DBP_WD_100K" in m])
-        folder = os.path.join(tmp, "BootEA_datasets", "BootEA_DBP_WD_100K") + "/"
+            z.extractall(tmp, [m for m in z.namelist() if "BootEA_%s_100K" % DATASET in m])
+        folder = os.path.join(tmp, "BootEA_datasets", "BootEA_%s_100K" % DATASET) + "/"
     args = load_args(os.path.join(REF, "code", "args.json"))
     args.training_data = folder
     args.retrain_literal_embeds = True
@@ -101,6 +103,7 @@ def main():
         out[key + "_w"] = a[:, 3].astype(np.float32)
     for k, v in out.items():
         print(k, getattr(v, "shape", v))
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT))
 
