@@ -129,6 +129,23 @@ def main():
         r = rank.cpu().numpy().astype(np.int64) + 1
         device_eval = {"hits@%d" % k: float((r <= k).mean() * 100) for k in (1, 5, 10, 50)}
         device_eval.update(mr=float(r.mean()), mrr=float((1.0 / r).mean()))
+        # ... and from the fp32 FMA tiles (the baseline implementation of the same evaluator): the tensor-core tiles
+        # (3xTF32) must not move a single Hits@k on the real rows; against the valid + test candidates too (valid())
+        from multike_b200 import _cabi
+        lib = _cabi.load()
+        cand = np.concatenate([valid[:, 1], g["test_links"][:, 1]]).astype(np.int32)
+        both = {}
+        for name, mode in (("tcgen05", 1), ("fma", 0)):
+            prev = lib.mke_sim_use_tensor_cores(mode)
+            rk, t1 = S.sim_rank(rv.ent.var, rv.ent.var, idx1=valid[:, 0].astype(np.int32), idx2=cand, normalize=True, dim=dim)
+            lib.mke_sim_use_tensor_cores(prev)
+            rr = rk.cpu().numpy().astype(np.int64) + 1
+            both[name] = {"rank": rr, "top1": t1.cpu().numpy(),
+                          "hits": {"hits@%d" % k: float((rr <= k).mean() * 100) for k in (1, 5, 10, 50)}}
+        device_eval["tcgen05_vs_fma"] = {
+            "candidates": int(len(cand)), "hits_tcgen05": both["tcgen05"]["hits"], "hits_fma": both["fma"]["hits"],
+            "ranks_equal_fraction": float((both["tcgen05"]["rank"] == both["fma"]["rank"]).mean()),
+            "top1_equal_fraction": float((both["tcgen05"]["top1"] == both["fma"]["top1"]).mean())}
     res = hits(E[valid[:, 0]], E[valid[:, 1]])
     summary = {"impl": args.impl, "epochs": args.epochs, "batch": B, "neg": K, "valid_links": int(len(valid)),
                "train_seconds": time.time() - t_start, **res, "log": log}
