@@ -169,58 +169,89 @@ class MultiKE:
         """MultiKE_model.py:203-221: weighted, own conv() weights"""
         self._ckga_attr_cnn, self._ckga_attr_slot = self._new_cnn(), "ckga_attribute"
 
-    def _attr_step(self, cnn, slot, rows, acc, weighted, scale):
-        """one session.run([loss, optimizer]) of an attribute graph on device rows [n, 4] (h, a, v, w)"""
-        ih, ia, iv = (rows[:, k].to(torch.int32).contiguous() for k in range(3))
-        w = rows[:, 3].to(torch.float32).contiguous() if weighted else None
+    # --- device-resident triple lists (SURVEY.md section 8 f-4) ------------------------------------------------
+    # The reference keeps every triple list as a Python list of tuples, re-reads it every epoch and shuffles it in
+    # place (MultiKE_model.py:314-315, :343-344).  Here a list is converted ONCE into int32 / fp32 column vectors in HBM
+    # (1.6 M attribute triples: 0.9 s of np.asarray per epoch otherwise, plus 1.3 s of random.shuffle); the copy is
+    # found again by the list object's identity and a fingerprint of its content, and the epoch's shuffle is a device
+    # permutation of the copy -- the Python list keeps its order, which nothing else reads.
+    def _device_columns(self, lst):
+        """(h, p, t int32 [n], w float32 [n]) of a list of (h, p, t[, w]) tuples, cached"""
+        cache = self.__dict__.setdefault("_list_cache", {})
+        n = len(lst)
+        mark = (n, tuple(lst[0]), tuple(lst[n // 2]), tuple(lst[-1])) if n else (0,)
+        hit = cache.get(id(lst))
+        if hit is not None and hit[0] is lst and hit[1] == mark:
+            return hit[2]
+        a = np.asarray(lst, dtype=np.float64)
+        if n == 0:
+            a = np.zeros((0, 4))
+        if a.shape[1] == 3:
+            a = np.concatenate([a, np.ones((n, 1))], 1)
+        cols = tuple(torch.from_numpy(np.ascontiguousarray(a[:, k], dtype=np.int32)).to(self.device) for k in range(3)) + \
+            (torch.from_numpy(np.ascontiguousarray(a[:, 3], dtype=np.float32)).to(self.device),)
+        if len(cache) > 16:
+            cache.clear()
+        cache[id(lst)] = (lst, mark, cols)
+        return cols
+
+    def _store_columns(self, lst, cols):
+        """the epoch's shuffle: the device copy is replaced by its permutation"""
+        hit = self._list_cache[id(lst)]
+        self._list_cache[id(lst)] = (hit[0], hit[1], cols)   # (a cached [n, 3] copy, if any, is dropped with the old order)
+
+    def _attr_step(self, cnn, slot, cols, acc, weighted, scale):
+        """one session.run([loss, optimizer]) of an attribute graph on device columns (h, a, v int32, w fp32)"""
+        ih, ia, iv, w = cols
+        if not weighted:
+            w = None
         cnn.fwd_bwd(self.av_ent_embeds, self.attr_embeds, self.literal_embeds, ih, ia, iv, acc, w=w, scale=scale)
         lr = self.args.learning_rate
         self.av_ent_embeds.apply_adagrad(slot, lr)
         self.attr_embeds.apply_adagrad(slot, lr)
         cnn.apply_adagrad(slot, lr)
 
-    @staticmethod
-    def _rows(triples, device):
-        a = np.asarray(triples, dtype=np.float64)
-        if a.ndim != 2 or a.shape[0] == 0:
-            return torch.zeros(0, 4, dtype=torch.float64, device=device)
-        if a.shape[1] == 3:
-            a = np.concatenate([a, np.ones((a.shape[0], 1))], 1)
-        return torch.from_numpy(np.ascontiguousarray(a[:, :4])).to(device)
-
     def train_attribute_view_1epo(self, epoch, triple_steps, steps_tasks, batch_queue, neighbors1, neighbors2):
         """MultiKE_model.py:319-345; batches as attr_batch.py:39-50 with neg_triples_num = 0"""
         start = time.time()
         pam = self.predicate_align_model
-        r1 = self._rows(pam.attribute_triples_w_weights1, self.device)
-        r2 = self._rows(pam.attribute_triples_w_weights2, self.device)
-        n1, n2 = r1.shape[0], r2.shape[0]
+        l1, l2 = pam.attribute_triples_w_weights1, pam.attribute_triples_w_weights2
+        c1, c2 = self._device_columns(l1), self._device_columns(l2)
+        n1, n2 = len(l1), len(l2)
         b1, b2 = split_batch(n1, n2, self.args.attribute_batch_size)
-        acc = T.new_loss_accumulator(self.device)
-        trained = 0
+        # the epoch's batches, attr_batch.py:39-50: step k = kg1 slice k ++ kg2 slice k; gathered ONCE into batch order,
+        # so that a step's batch is a contiguous view
+        bounds, order, pos = [], [], 0
         for step in range(triple_steps):
             (s1, e1), (s2, e2) = clipped_slice(n1, b1, step), clipped_slice(n2, b2, step)
-            rows = torch.cat([r1[s1:e1], r2[s2:e2]])
-            if rows.shape[0] == 0:
+            bounds.append((pos, pos + (e1 - s1) + (e2 - s2)))
+            pos += (e1 - s1) + (e2 - s2)
+            order += [(0, s1, e1), (1, s2, e2)]
+        epoch_cols = tuple(torch.cat([(c1, c2)[which][k][s:e] for which, s, e in order]) for k in range(4))
+        acc = T.new_loss_accumulator(self.device)
+        trained = 0
+        for lo, hi in bounds:
+            if hi == lo:
                 continue
-            self._attr_step(self._attr_cnn, self._attr_slot, rows, acc, weighted=True, scale=1.0)
-            trained += rows.shape[0]
+            self._attr_step(self._attr_cnn, self._attr_slot, tuple(c[lo:hi] for c in epoch_cols), acc, weighted=True, scale=1.0)
+            trained += hi - lo
         epoch_loss = float(acc.item()) / max(trained, 1)
-        import random
-        random.shuffle(pam.attribute_triples_w_weights1)
-        random.shuffle(pam.attribute_triples_w_weights2)
+        # random.shuffle of both lists (:343-344), on the device copies
+        p1, p2 = torch.randperm(n1, device=self.device), torch.randperm(n2, device=self.device)
+        self._store_columns(l1, tuple(c[p1] for c in c1))
+        self._store_columns(l2, tuple(c[p2] for c in c2))
         print('epoch {} of att. view, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss, time.time() - start))
         return epoch_loss
 
     def _attr_sampled_epoch(self, sup_triples, cnn, slot, weighted, scale):
-        rows = self._rows(sup_triples, self.device)
-        n = rows.shape[0]
+        cols = self._device_columns(sup_triples)
+        n = len(sup_triples)
         steps = int(math.ceil(n / self.args.attribute_batch_size))
         batch_size = self.args.attribute_batch_size if steps > 1 else n
         acc = T.new_loss_accumulator(self.device)
         for _ in range(steps):
             pick = torch.randperm(n, device=self.device)[:batch_size]  # random.sample
-            self._attr_step(cnn, slot, rows[pick], acc, weighted=weighted, scale=scale)
+            self._attr_step(cnn, slot, tuple(c[pick] for c in cols), acc, weighted=weighted, scale=scale)
         return float(acc.item()) / max(steps * batch_size, 1)
 
     def train_cross_kg_entity_inference_attribute_view_1epo(self, epoch, sup_triples):
@@ -381,12 +412,16 @@ class MultiKE:
         """MultiKE_model.py:349-369 / 393-414: `steps` batches of random.sample(sup_triples, B),
         loss = 2 * [weighted] logistic loss without negatives, Adagrad slots of this graph."""
         rv = self._rv
-        pos, w = _triples(sup_triples, with_weight=weighted)
-        n = pos.shape[0]
+        h, r, t, w_d = self._device_columns(sup_triples)
+        entry = self._list_cache[id(sup_triples)]
+        if len(entry) == 3:   # the [n, 3] rows next to the columns, same lifetime
+            entry = self._list_cache[id(sup_triples)] = entry + (torch.stack([h, r, t], 1).contiguous(),)
+        pos_d = entry[3]
+        n = pos_d.shape[0]
+        if not weighted:
+            w_d = None
         steps = int(math.ceil(n / self.args.batch_size))
         batch_size = self.args.batch_size if steps > 1 else n
-        pos_d = torch.from_numpy(pos).to(rv.device)
-        w_d = None if w is None else torch.from_numpy(w).to(rv.device)
         acc = T.new_loss_accumulator(rv.device)
         trained = 0
         for _ in range(steps):

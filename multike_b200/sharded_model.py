@@ -150,9 +150,11 @@ class _ShardedModel:
         self.rel_embeds = self._rv.rel
 
     # --- steps -----------------------------------------------------------------------------------
-    def _attr_step(self, cnn, slot, rows, acc, weighted, scale):
-        ih, ia, iv = (rows[:, k].to(torch.int32).contiguous() for k in range(3))
-        w = rows[:, 3].to(torch.float32).contiguous() if weighted else None
+    def _attr_step(self, cnn, slot, cols, acc, weighted, scale):
+        ih, ia, iv, w = cols
+        ih = ih.contiguous()
+        if not weighted:
+            w = None
         staged, loc = self.av_ent_embeds.stage(ih)
         self._barrier.wait()   # every rank holds its copy of the batch's rows: updates may begin
         cnn.fwd_bwd(staged, self.attr_embeds, self.literal_embeds, loc, ia, iv, acc, w=w, scale=scale)

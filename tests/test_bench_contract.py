@@ -1,7 +1,6 @@
 """bench.py's JSON contract, checked without a GPU: the reference arm (`--impl reference`, the oracle
-port of the reference's CPU path) is run for one bounded step, and the committed line of the B200
-arm (profiles/r1_bench_default.json, written by `python bench.py` on a B200) is checked for every
-key the driver reads."""
+port of the reference's CPU path) is run for one bounded step.  The B200 arm's line is checked live by
+tests/test_gpu_bench.py."""
 import json
 import os
 import subprocess
@@ -25,23 +24,3 @@ def test_reference_arm_prints_one_json_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["sample"]
     assert j["cpu_baseline"]["value"] == j["value"] == j["e2e"]["value"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
-
-
-def test_recorded_b200_line_has_the_contract_keys():
-    j = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_default.json")))
-    assert BASE_KEYS | {"clocks", "roofline"} <= set(j) and "impl" not in j
-    assert j["n_gpus"] == 1 and j["warmup"] >= 3 and j["dtype"] == "f32" and j["data"] == "synthetic"
-    assert j["config"]["workload"] == "dwy100k_rel_d75_b20000_k10" and "model" not in j["config"]
-    r = j["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["traffic"] is None or r["traffic"] > 0
-    # achieved = algorithmic bytes per launch / mean launch duration
-    assert abs(r["achieved"] - r["algorithmic_bytes"] / (r["launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
-    e = j["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != j["value"]
-    assert j["gpu_launches"] >= 2 * j["steps"]
-    assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    c = j["cpu_baseline"]
-    assert c["kind"] in ("port", "reference") and c["unit"] == j["unit"] and c["cores"] >= 1
-    # value = positives / time: ms_per_step x value = positives per step (the 46-step epoch's mean batch)
-    assert abs(j["value"] * j["ms_per_step"] * 1e-3 - r["algorithmic_bytes"] / r["bytes_per_positive"]) < 1.0

@@ -97,7 +97,8 @@ def parse(text):
         if line.endswith("results:"):
             label = line.strip()
         elif "avg. loss" in line:
-            losses.append((line.split(",")[0], float(NUM.findall(line.split("avg. loss:")[1])[0])))
+            nums = NUM.findall(line.split("avg. loss:")[1])   # loss, then the epoch part's wall-clock seconds
+            losses.append((line.split(",")[0], float(nums[0]), float(nums[1]) if len(nums) > 1 else None))
         elif "results: hits@" in line:
             body = line.split("] = ")[1].split(", time")[0]   # "[h1 h5 h10 h50]%, mr = .., mrr = .."
             hits.append((label, [float(x) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", body)]))
@@ -169,6 +170,10 @@ def main():
             with open(a.out, "w") as fh:
                 json.dump(rec, fh)
         print(json.dumps({k: rec[k] for k in ("dataset", "gpus", "seconds")}), "losses", len(losses), "final hits", hits[-1] if hits else None)
+        last = {}
+        for label, _, secs_part in losses:   # seconds of each part of the LAST epoch (the first one pays the conversions)
+            last[label.split(" of ", 1)[1]] = secs_part
+        print("seconds per epoch part (last epoch):", json.dumps(last))
     if world > 1:
         m.close()
         dist.destroy_process_group()
