@@ -499,6 +499,11 @@ int mke_rel_step_structured4(const mke_table_t* ent, const mke_table_t* rel, con
                              int32_t pos_own_lo, int32_t pos_own_hi, const float* w_or_null, float pos_scale,
                              double* loss_accum, int32_t variant, mke_stream_t stream);
 
+/* random.sample(range(n), count) of the reference's cross-KG / entity batches (MultiKE_model.py:355-358, :377, :399,
+ * :443, :462): out[i], i < count, = distinct uniform indices of [0, n) -- the first images of a keyed pseudo-random
+ * permutation (Feistel network, cycle walking), a function of (seed, draw) only. */
+int mke_sample_distinct(int32_t n, int32_t count, uint64_t seed, uint64_t draw, int32_t* out, mke_stream_t stream);
+
 int mke_peer_alloc(uint64_t bytes, void** ptr);                  /* cudaMalloc + zero fill          */
 int mke_peer_free(void* ptr);
 int mke_ipc_export(const void* ptr, unsigned char handle[64]);   /* cudaIpcGetMemHandle             */

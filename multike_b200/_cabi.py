@@ -146,6 +146,7 @@ SIGNATURES = {
     "mke_ipc_export": (_i32, [_vp, _c.c_char_p]),
     "mke_ipc_open": (_i32, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "mke_ipc_close": (_i32, [_vp]),
+    "mke_sample_distinct": (_i32, [_i32, _i32, _c.c_uint64, _c.c_uint64, _vp, _vp]),
     "mke_table_stage_rows": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "mke_table_commit_grads": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "mke_peer_barrier": (_i32, [_vp, _i32, _i32, _c.c_uint32, _vp]),

@@ -41,6 +41,8 @@ struct GemmParams {
   const float* bias;  // [N] or NULL
   float* C;
   long long ldc;
+  int kb_per_split;   // k-blocks (of 32) per CTA along grid z (split-K); >= all of them: no split
+  int accumulate;     // 1: C += result with atomic adds (split-K partial sums, or a gradient accumulator)
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -53,7 +55,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kGemmStages + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * kGemmBN;
-  const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  const int all_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  const int kb0 = blockIdx.z * p.kb_per_split;                                   // this CTA's K range (split-K)
+  const int num_kb = all_kb - kb0 < p.kb_per_split ? all_kb - kb0 : p.kb_per_split;
   auto full = [&](int s) { return smem_u32(bars + s); };
   auto empty = [&](int s) { return smem_u32(bars + kGemmStages + s); };
   auto accum_full = [&](int b) { return smem_u32(bars + 2 * kGemmStages + b); };
@@ -90,10 +94,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         mbar_wait(empty(s), ph ^ 1u);
         mbar_expect_tx(full(s), kGemmStageBytes);
         const uint32_t dst = smem_u32(smem + s * kGemmStageBytes);
-        tma_load_2d(&map_a_hi, full(s), dst + 0 * kGemmTileBytes, kb * kGemmBK, m0);
-        tma_load_2d(&map_a_lo, full(s), dst + 1 * kGemmTileBytes, kb * kGemmBK, m0);
-        tma_load_2d(&map_b_hi, full(s), dst + 2 * kGemmTileBytes, kb * kGemmBK, n0);
-        tma_load_2d(&map_b_lo, full(s), dst + 3 * kGemmTileBytes, kb * kGemmBK, n0);
+        tma_load_2d(&map_a_hi, full(s), dst + 0 * kGemmTileBytes, (kb0 + kb) * kGemmBK, m0);
+        tma_load_2d(&map_a_lo, full(s), dst + 1 * kGemmTileBytes, (kb0 + kb) * kGemmBK, m0);
+        tma_load_2d(&map_b_hi, full(s), dst + 2 * kGemmTileBytes, (kb0 + kb) * kGemmBK, n0);
+        tma_load_2d(&map_b_lo, full(s), dst + 3 * kGemmTileBytes, (kb0 + kb) * kGemmBK, n0);
       }
     }
   } else if (warp == 1) {
@@ -155,7 +159,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
       for (int j = 0; j < kGemmBN; ++j) {
         const int col = n0 + j;
-        if (col < p.N) out[j] = acc[j] + (p.bias != nullptr ? __ldg(p.bias + col) : 0.f);
+        if (col < p.N) {
+          const float v = acc[j] + ((p.bias != nullptr && blockIdx.z == 0) ? __ldg(p.bias + col) : 0.f);
+          if (p.accumulate)
+            atomicAdd(out + j, v);
+          else
+            out[j] = v;
+        }
       }
     }
   }
@@ -188,14 +198,17 @@ extern "C" int mke_split_tf32(const float* x, float* hi, float* lo, int64_t n, m
   return 0;
 }
 
-extern "C" int mke_gemm_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
-                               int64_t ldb, int32_t M, int32_t N, int32_t K, const float* bias_or_null, float* C,
-                               int64_t ldc, mke_stream_t stream) {
+namespace mke {
+// C (+)= A . B^T (+ bias), optionally split along K over grid z (then C must accumulate)
+int gemm_tf32x3_launch(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                       int M, int N, int K, const float* bias_or_null, float* C, int64_t ldc, int k_splits, int accumulate,
+                       cudaStream_t stream) {
   MKE_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad GEMM shape %d x %d x %d", M, N, K);
   MKE_CHECK_ARG(a_hi && a_lo && b_hi && b_lo && C, "null operand");
   MKE_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "leading dimensions");
   MKE_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "lda / ldb must be multiples of 4 floats (TMA: 16-byte row pitch)");
   MKE_CHECK_ARG(((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) % 16 == 0, "operands must be 16-byte aligned");
+  MKE_CHECK_ARG(k_splits >= 1 && (k_splits == 1 || accumulate), "split-K needs an accumulating epilogue");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int rc = make_map(&ma_hi, a_hi, M, K, lda)) return rc;
   if (int rc = make_map(&ma_lo, a_lo, M, K, lda)) return rc;
@@ -208,9 +221,20 @@ extern "C" int mke_gemm_tf32x3(const float* a_hi, const float* a_lo, int64_t lda
       return cuda_fail(e, "cudaFuncSetAttribute(gemm_tf32x3_kernel)");
     configured = true;
   }
-  const GemmParams p{M, N, K, bias_or_null, C, (long long)ldc};
-  const dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + kGemmBN - 1) / kGemmBN);
-  gemm_tf32x3_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  const int all_kb = (K + kGemmBK - 1) / kGemmBK;
+  if (k_splits > all_kb) k_splits = all_kb;
+  const int per = (all_kb + k_splits - 1) / k_splits;
+  k_splits = (all_kb + per - 1) / per;  // no empty split
+  const GemmParams p{M, N, K, bias_or_null, C, (long long)ldc, per, accumulate};
+  const dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + kGemmBN - 1) / kGemmBN, k_splits);
+  gemm_tf32x3_kernel<<<grid, kGemmThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   MKE_CHECK_LAUNCH("gemm_tf32x3_kernel");
   return 0;
+}
+}  // namespace mke
+
+extern "C" int mke_gemm_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo,
+                               int64_t ldb, int32_t M, int32_t N, int32_t K, const float* bias_or_null, float* C,
+                               int64_t ldc, mke_stream_t stream) {
+  return gemm_tf32x3_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias_or_null, C, ldc, 1, 0, (cudaStream_t)stream);
 }

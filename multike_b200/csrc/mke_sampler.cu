@@ -327,3 +327,44 @@ extern "C" int mke_neg_keep_owned2(int32_t* neg_ent, uint32_t* neg_side, int32_t
   MKE_CHECK_LAUNCH("neg_keep_owned_compact_kernel");
   return 0;
 }
+
+// ---- random.sample(range(n), count) without a sort ------------------------------------------------------------------
+// The cross-KG / entity batches of the reference are random.sample(list, B) every step (MultiKE_model.py:355-358, :377,
+// :399, :422, :443, :462).  A sample without replacement is the first `count` images of a random permutation of [0, n):
+// here a keyed Feistel network over the smallest even-width power-of-two domain >= n, cycle-walked back into [0, n)
+// (a bijection for every key; 3.5 us for 5 000 picks where torch.randperm(n)[:B] sorts n keys: 135 us at n = 554 173).
+namespace mke {
+__device__ __forceinline__ uint32_t feistel_permute(uint32_t x, int half_bits, uint64_t key) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+  for (int round = 0; round < 6; ++round) {
+    const uint32_t f = (uint32_t)(mix64(key + (uint64_t)(round + 1) * kGamma + r) >> 20) & mask;
+    const uint32_t nl = r;
+    r = l ^ f;
+    l = nl;
+  }
+  return (l << half_bits) | r;
+}
+__global__ void sample_distinct_kernel(uint32_t n, int count, int half_bits, uint64_t key, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint32_t x = (uint32_t)i;
+  do {
+    x = feistel_permute(x, half_bits, key);
+  } while (x >= n);  // cycle walking: the domain is < 4 n, so two tries on average at most
+  out[i] = (int32_t)x;
+}
+}  // namespace mke
+
+extern "C" int mke_sample_distinct(int32_t n, int32_t count, uint64_t seed, uint64_t draw, int32_t* out, mke_stream_t stream) {
+  MKE_CHECK_ARG(n > 0 && count >= 0 && count <= n, "count=%d outside [0, n=%d]", count, n);
+  if (count == 0) return 0;
+  MKE_CHECK_ARG(out, "null output");
+  int half_bits = 1;
+  while ((1ull << (2 * half_bits)) < (unsigned long long)n) ++half_bits;
+  const uint64_t key = mke::stream_key(seed ^ 0x5DEECE66Dull, draw);
+  mke::sample_distinct_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint32_t)n, count, half_bits, key, out);
+  MKE_CHECK_LAUNCH("sample_distinct_kernel");
+  return 0;
+}

@@ -175,6 +175,11 @@ class MultiKE:
     # (1.6 M attribute triples: 0.9 s of np.asarray per epoch otherwise, plus 1.3 s of random.shuffle); the copy is
     # found again by the list object's identity and a fingerprint of its content, and the epoch's shuffle is a device
     # permutation of the copy -- the Python list keeps its order, which nothing else reads.
+    def _pick(self, n, count):
+        """random.sample(range(n), count) on the device (mke_sample_distinct): the reference's per-step batch draw"""
+        self._draws = getattr(self, "_draws", 0) + 1
+        return T.sample_distinct(n, count, self.seed, self._draws, self.device)
+
     def _device_columns(self, lst):
         """(h, p, t int32 [n], w float32 [n]) of a list of (h, p, t[, w]) tuples, cached"""
         cache = self.__dict__.setdefault("_list_cache", {})
@@ -250,7 +255,7 @@ class MultiKE:
         batch_size = self.args.attribute_batch_size if steps > 1 else n
         acc = T.new_loss_accumulator(self.device)
         for _ in range(steps):
-            pick = torch.randperm(n, device=self.device)[:batch_size]  # random.sample
+            pick = self._pick(n, batch_size)  # random.sample
             self._attr_step(cnn, slot, tuple(c[pick] for c in cols), acc, weighted=weighted, scale=scale)
         return float(acc.item()) / max(steps * batch_size, 1)
 
@@ -324,7 +329,7 @@ class MultiKE:
         ws = torch.empty(int(lib.mke_space_mapping_workspace_floats(batch_size, dim)), dtype=torch.float32,
                          device=self.device)
         for _ in range(steps):
-            idx = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()  # random.sample: distinct ids
+            idx = ents[self._pick(n, batch_size)].contiguous()  # random.sample: distinct ids
             self._space_step(idx, ws, total, lr, ow)
         epoch_loss = float(total) / max(steps * batch_size, 1)
         print('epoch {} of shared space learning, avg. loss: {:.4f}, time: {:.4f}s'.format(epoch, epoch_loss,
@@ -349,7 +354,7 @@ class MultiKE:
         lr, cvw = self.args.ITC_learning_rate, float(self.args.cv_weight)
         trained = 0
         for _ in range(steps):
-            pick = ents[torch.randperm(n, device=self.device)[:batch_size]].contiguous()  # random.sample
+            pick = ents[self._pick(n, batch_size)].contiguous()  # random.sample
             self._align_step(pick, acc, lr, cvw)
             trained += batch_size
         # the fetched cross_name_loss is the un-weighted sum (the optimizer minimises cv_weight * loss)
@@ -425,7 +430,7 @@ class MultiKE:
         acc = T.new_loss_accumulator(rv.device)
         trained = 0
         for _ in range(steps):
-            pick = torch.randperm(n, device=rv.device)[:batch_size]  # random.sample: without replacement
+            pick = self._pick(n, batch_size)  # random.sample: without replacement
             self._positives_only_step(pos_d[pick].contiguous(), None if w_d is None else w_d[pick].contiguous(), acc, slot)
             trained += batch_size
         return float(acc.item()) / max(trained, 1)

@@ -291,6 +291,15 @@ def apply_adagrad_pair(table_a, acc_a, lr_a, table_b, acc_b, lr_b):
                                                 float(lr_b), _cabi.current_stream()))
 
 
+def sample_distinct(n, count, seed, draw, device="cuda"):
+    """mke_sample_distinct: random.sample(range(n), count) as int64 indices on the device (no sort)"""
+    lib = _cabi.load()
+    out = torch.empty(int(count), dtype=torch.int32, device=device)
+    _cabi.check(lib.mke_sample_distinct(int(n), int(count), int(seed) & (2 ** 64 - 1), int(draw) & (2 ** 64 - 1),
+                                        out.data_ptr(), _cabi.current_stream()))
+    return out.long()
+
+
 def sample_uniform(pos1, kg1, pos2, kg2, K, seed, step, device="cuda"):
     """mke_sample_uniform: the negatives the fused kernel would draw, as [(len1+len2)*K, 3]."""
     lib = _cabi.load()

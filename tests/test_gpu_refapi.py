@@ -353,3 +353,25 @@ def test_drivers_run_itc_and_ssl_schedules(capsys, tmp_path):
     assert [p for p, _ in pam.updates] == ["relation", "attribute"] * 2   # epochs 2 and 4
     # three short epochs of space mapping do not align the shared space yet: only the views are checked
     assert _hits1_lines(out, "avg")[-1] > 10.0 and len(_hits1_lines(out, "final")) == 2
+
+
+@pytest.mark.parametrize("n,count", [(1, 1), (7, 7), (1000, 1000), (554173, 5000), (200000, 5000), (65536, 65536)])
+def test_sample_distinct_is_a_sample_without_replacement(n, count):
+    """mke_sample_distinct = random.sample(range(n), count) (the reference's cross-KG / entity batch draw): distinct indices
+    of [0, n), a function of (seed, draw) only, a full permutation at count == n, and uniform (mean / spread / a chi-square
+    over 16 bins of many draws)"""
+    from multike_b200 import tables as T
+    a = T.sample_distinct(n, count, seed=3, draw=1).cpu().numpy()
+    assert a.shape == (count,) and a.min() >= 0 and a.max() < n and len(np.unique(a)) == count
+    assert np.array_equal(a, T.sample_distinct(n, count, seed=3, draw=1).cpu().numpy())
+    b = T.sample_distinct(n, count, seed=3, draw=2).cpu().numpy()
+    if n > 1000:
+        assert not np.array_equal(a, b) and len(np.intersect1d(a, b)) < count
+    if n >= 200000:
+        draws = np.concatenate([T.sample_distinct(n, count, seed=11, draw=k).cpu().numpy() for k in range(40)])
+        hist = np.bincount(draws * 16 // n, minlength=16).astype(np.float64)
+        expect = len(draws) / 16
+        assert ((hist - expect) ** 2 / expect).sum() < 45.0          # chi-square, 15 degrees of freedom (p ~ 1e-4)
+        assert abs(draws.mean() / n - 0.5) < 0.01
+        # positions are independent of the output order: first and second half of a draw are alike
+        assert abs(a[: count // 2].mean() - a[count // 2:].mean()) / n < 0.03
