@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kSmThreads) space_pass_a_kernel(const SmParams
   const int tiles = (p.n + kSmRows - 1) / kSmRows;
   constexpr int kMaxOwn = (kSmMaxDim * kSmMaxDim + kSmThreads - 1) / kSmThreads;  // entries of a d x d matrix per thread
   const int own = (d * d + kSmThreads - 1) / kSmThreads;
-  for (int k = 0; k < 3; ++k) {
+  {
+    const int k = blockIdx.y;  // one view per grid row: the three views run side by side
     for (int e = tid; e < d * d; e += kSmThreads) sM[(e / d) * ld + (e % d)] = __ldg(p.maps + (size_t)k * d * d + e);
     float g1[kMaxOwn], g2[kMaxOwn];
 #pragma unroll
@@ -141,8 +142,9 @@ __global__ void __launch_bounds__(kSmThreads) space_pass_a_kernel(const SmParams
   }
 }
 
-// one block: per view the scalars, the mapping gradient and the loss
-__global__ void __launch_bounds__(kSmThreads) space_finalize_kernel(const SmParams p) {
+// one block per view: the scalars, the mapping gradient and the view's share of the loss
+constexpr int kSmFinThreads = 1024;
+__global__ void __launch_bounds__(kSmFinThreads) space_finalize_kernel(const SmParams p) {
   extern __shared__ float sm[];
   const int d = p.dim, ld = p.ld;
   float* sM = sm;            // [d][ld]
@@ -151,13 +153,14 @@ __global__ void __launch_bounds__(kSmThreads) space_finalize_kernel(const SmPara
   const int tid = threadIdx.x;
   if (tid == 0) s_loss = 0.0;
   const double f2 = p.sc[6];
-  for (int k = 0; k < 3; ++k) {
+  {
+    const int k = blockIdx.x;  // one block per view
     __syncthreads();
     const float* M = p.maps + (size_t)k * d * d;
-    for (int e = tid; e < d * d; e += kSmThreads) sM[(e / d) * ld + (e % d)] = M[e];
+    for (int e = tid; e < d * d; e += kSmFinThreads) sM[(e / d) * ld + (e % d)] = M[e];
     __syncthreads();
     float orth = 0.f, nrm = 0.f;
-    for (int e = tid; e < d * d; e += kSmThreads) {
+    for (int e = tid; e < d * d; e += kSmFinThreads) {
       const int a = e / d, b = e % d;
       float acc = 0.f;
       for (int q = 0; q < d; ++q) acc = fmaf(sM[a * ld + q], sM[b * ld + q], acc);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kSmThreads) space_finalize_kernel(const SmPara
     const float rf = (float)r, r3t = below ? 0.f : (float)(r * r * r * t);
     const float* G1 = p.G + ((size_t)k * 2 + 0) * d * d;
     const float* G2 = p.G + ((size_t)k * 2 + 1) * d * d;
-    for (int e = tid; e < d * d; e += kSmThreads) {
+    for (int e = tid; e < d * d; e += kSmFinThreads) {
       const int a = e / d, b = e % d;
       float pm = 0.f;  // ((M M^T - I) M)[a][b]
       for (int q = 0; q < d; ++q) pm = fmaf(sP[a * ld + q], sM[q * ld + b], pm);
@@ -278,9 +281,9 @@ extern "C" int mke_space_mapping_fwd_bwd(const mke_table_t* shared, const mke_ta
   }
   const int tiles = (n + kSmRows - 1) / kSmRows;
   const int blocks_a = tiles < sm_count() ? tiles : sm_count();
-  space_pass_a_kernel<<<blocks_a, kSmThreads, smem_a, s>>>(p);
+  space_pass_a_kernel<<<dim3(blocks_a, 3), kSmThreads, smem_a, s>>>(p);
   MKE_CHECK_LAUNCH("space_pass_a_kernel");
-  space_finalize_kernel<<<1, kSmThreads, smem_f, s>>>(p);
+  space_finalize_kernel<<<3, kSmFinThreads, smem_f, s>>>(p);
   MKE_CHECK_LAUNCH("space_finalize_kernel");
   int blocks_b = (n + kSmThreads / 32 - 1) / (kSmThreads / 32);
   if (blocks_b > sm_count() * 8) blocks_b = sm_count() * 8;
