@@ -23,11 +23,9 @@ The result equals the single-GPU drivers (refapi.drivers) up to fp32 summation o
 compares the per-epoch losses and the evaluation of both.
 """
 import ctypes
-import math
 import random
 import time
 
-import numpy as np
 import torch
 
 from . import _cabi
