@@ -205,7 +205,12 @@ def run_sharded(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     import ctypes
+    from multike_b200.sharded_model import PeerBarrier
     lib = _cabi.load()
+    # a device-side flag barrier in front of each timed region: the ranks leave dist.barrier() + synchronize() hundreds of
+    # microseconds apart, and a rank that starts early would otherwise spend that skew INSIDE its timed region, waiting in
+    # the first step's barrier for the GPU of the rank whose host is late
+    align = PeerBarrier(dist.group.WORLD)
     sv.train_steps(0, warmup)
     step_no = warmup
     clocks = ClockSampler(local_rank)
@@ -216,6 +221,7 @@ def run_sharded(args, rank, world, local_rank):
     _cabi.check(lib.mke_timing_stride(max(1, args.p1_every)))
     launches0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align.wait()
     e0.record()
     positives = sv.train_steps(step_no % spe, args.steps)
     e1.record()
@@ -234,6 +240,7 @@ def run_sharded(args, rank, world, local_rank):
     step_no += 3
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align.wait()
     f0.record()
     e2e_pos = sv.train_steps(step_no % spe, args.steps, host_fed=True)
     f1.record()
@@ -260,6 +267,8 @@ def run_sharded(args, rank, world, local_rank):
                        "triples": int(sv.n1 + sv.n2), "dim": dim, "batch": B, "global_batch": B * world, "neg": K,
                        "steps_per_epoch": spe, "variant": VARIANT_NAME[sv.variant],
                        "l2": "no flush: per-rank working set exceeds L2 / rows come over NVLink",
+                       "rank_alignment": "each timed region starts behind a device-side flag barrier of all ranks (after "
+                                         "dist.barrier() + synchronize()), so host-side exit skew is not timed",
                        "parallelism": "entity table row-sharded over %d GPUs, KG-block placement (each KG on half of "
                                       "the ranks; %s; peer gathers + peer reductions inside phase 1), relation "
                                       "gradient bucket summed through peer memory, flag barriers, C-side step loop" % (
@@ -277,6 +286,7 @@ def run_sharded(args, rank, world, local_rank):
                          "peak_source": peak_kind, "launch_ms": p1_ms, "bytes_per_positive": bytes_per_positive(dim, K)},
         }
         print(json.dumps(line))
+    align.close()
     sv.close()
     dist.destroy_process_group()
     return 0
