@@ -180,3 +180,33 @@ def sample_batch_fast(pos1, kg1, pos2, kg2, K, seed, step, index_base=0):
         out[off * K:(off + n) * K] = block.reshape(n * K, 3)
         off += n
     return out
+
+
+# ---- mke_sample_distinct (csrc/mke_sampler.cu): random.sample(range(n), count) as the first images of a keyed Feistel
+# permutation with cycle walking -- restated bit-exactly.  (The reference draws these batches with random.sample,
+# MultiKE_model.py:355-358, :377, :399, :443, :462; its CPython stream is not reproduced, the semantics -- distinct,
+# uniform indices -- are what the tests check.)
+def _feistel_permute(x, half_bits, key):
+    mask = (1 << half_bits) - 1
+    left, right = x >> half_bits, x & mask
+    for rnd in range(6):
+        f = (mix64((key + (rnd + 1) * GAMMA + right) & MASK) >> 20) & mask
+        left, right = right, left ^ f
+    return (left << half_bits) | right
+
+
+def sample_distinct(n, count, seed, draw):
+    """[count] distinct indices of [0, n): what mke_sample_distinct returns for (seed, draw)"""
+    half_bits = 1
+    while (1 << (2 * half_bits)) < n:
+        half_bits += 1
+    key = stream_key((seed ^ 0x5DEECE66D) & MASK, draw)
+    out = []
+    for i in range(count):
+        x = i
+        while True:
+            x = _feistel_permute(x, half_bits, key)
+            if x < n:
+                break
+        out.append(x)
+    return out

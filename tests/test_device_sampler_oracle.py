@@ -127,3 +127,19 @@ def test_attribute_head_sampler_semantics_match_reference(golden):
     # index_base shifts the RNG coordinates: a rank holding positions [60, 120) draws the same
     part = ds.sample_attribute_heads(trip[60:120], kg, np.zeros((0, 3)), kg, K, seed=2, step=1, index_base=60)
     assert np.array_equal(part, neg[60:])
+
+
+def test_sample_distinct_restatement_is_a_permutation_prefix():
+    """oracle restatement of mke_sample_distinct: distinct indices, a permutation of range(n) at count == n, a
+    function of (seed, draw); the GPU test compares the kernel with it bit for bit"""
+    from oracle import device_sampler as ds
+    for n in (1, 2, 7, 64, 1000, 4097):
+        full = ds.sample_distinct(n, n, seed=5, draw=3)
+        assert sorted(full) == list(range(n))
+        assert ds.sample_distinct(n, min(n, 17), seed=5, draw=3) == full[:min(n, 17)]
+    a, b = ds.sample_distinct(5000, 300, 5, 1), ds.sample_distinct(5000, 300, 5, 2)
+    assert a != b and len(set(a)) == 300
+    # uniform: mean position of many draws
+    import numpy as np
+    draws = np.concatenate([ds.sample_distinct(10007, 50, 9, k) for k in range(60)])
+    assert abs(draws.mean() / 10007 - 0.5) < 0.03

@@ -363,6 +363,8 @@ def test_sample_distinct_is_a_sample_without_replacement(n, count):
     from multike_b200 import tables as T
     a = T.sample_distinct(n, count, seed=3, draw=1).cpu().numpy()
     assert a.shape == (count,) and a.min() >= 0 and a.max() < n and len(np.unique(a)) == count
+    from oracle import device_sampler as ds   # index work: bit-exact against the CPU restatement
+    assert a[:200].tolist() == ds.sample_distinct(n, min(count, 200), 3, 1)
     assert np.array_equal(a, T.sample_distinct(n, count, seed=3, draw=1).cpu().numpy())
     b = T.sample_distinct(n, count, seed=3, draw=2).cpu().numpy()
     if n > 1000:
