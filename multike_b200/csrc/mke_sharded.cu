@@ -118,7 +118,12 @@ __global__ void __launch_bounds__(kXThreads) rel_exchange_kernel(const ExchangeP
   }
 }
 
-__global__ void peer_barrier_kernel(const PeerSync ps, uint32_t seq) { peer_barrier(ps, seq); }
+// barrier C; host fed: this rank's share of the step loss goes to pinned host memory by a store of the kernel (a
+// cudaMemcpyAsync of 8 bytes per step on the main stream costs the step a copy-engine round trip)
+__global__ void peer_barrier_kernel(const PeerSync ps, uint32_t seq, const double* loss_src, double* loss_host) {
+  if (threadIdx.x == 0 && loss_host != nullptr) *reinterpret_cast<volatile double*>(loss_host) = *loss_src;
+  peer_barrier(ps, seq);
+}
 
 // ---- which positives a rank trains in a global step (sharded.py: rank_parts / group_parts) ------------------------
 struct Plan {
@@ -262,6 +267,14 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
                                  v->rank, v->dummy_row, v->neg_valid[buf], st);
     return 0;
   };
+  double* host_loss_dev = nullptr;  // the pinned loss buffer as the device sees it
+  if (v->host_step_loss != nullptr) {
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, (void*)v->host_step_loss, 0) == cudaSuccess)
+      host_loss_dev = (double*)d;
+    else
+      cudaGetLastError();
+  }
   long long positives = 0;
   int rc = 0;
   Plan cur = make_plan(v, first_step % steps_per_epoch);
@@ -279,7 +292,7 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
                                     nullptr, 1.0f, v->step_loss + s, v->variant, main);
       if (timed) timer_end(main);
       if (rc) break;
-      if (v->host_step_loss != nullptr)  // this rank's share of the step loss, back to the host every step
+      if (v->host_step_loss != nullptr && host_loss_dev == nullptr)  // (pinned memory the device cannot address: copy)
         if (cudaError_t e = cudaMemcpyAsync(v->host_step_loss + s, v->step_loss + s, sizeof(double), cudaMemcpyDeviceToHost, main)) {
           rc = cuda_fail(e, "D2H loss");
           break;
@@ -305,7 +318,9 @@ extern "C" int mke_rel_sharded_train_steps(const mke_rel_sharded_view_t* v, int3
     }
     rc = mke_rows_apply_adagrad_pair(v->ent, v->ent_acc, v->lr, v->rel, v->rel_acc, v->lr, main);
     if (rc) break;
-    peer_barrier_kernel<<<1, 32, 0, main>>>(x.ps, x.seq + 1u);
+    // this rank's share of the step loss, back to the host every step: stored by the barrier kernel
+    peer_barrier_kernel<<<1, 32, 0, main>>>(x.ps, x.seq + 1u, v->step_loss + s,
+                                            (host_loss_dev != nullptr && n > 0) ? host_loss_dev + s : nullptr);
     count_launch();
     if (cudaError_t e = cudaGetLastError()) { rc = cuda_fail(e, "peer_barrier_kernel"); break; }
     if (have_next && ahead) cudaStreamWaitEvent(main, ev_ready, 0);
