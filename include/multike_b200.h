@@ -215,8 +215,10 @@ int mke_rows_apply_adagrad_pair(const mke_table_t* a, float* acc_a, float lr_a,
  *   gamma[D] beta[D] k1[2][4][1][2] b1[2] k2[2][4][2][2] b2[2] wd[4D][D] bd[D]
  * (22 777 at D = 75; three independent instances exist in the reference).
  * Gradient rows go to ent->grad / attr->grad as in the other kernels; gtheta is accumulated (+=).
- * workspace: mke_attr_cnn_workspace_floats(n, dim) floats.  Phase 2: mke_rows_apply_adagrad for the
- * tables, mke_dense_apply_adagrad for theta (acc0 = 0.1).
+ * workspace: mke_attr_cnn_workspace_floats(n, dim) floats, 16-byte aligned (activations as TF32 part + remainder, their
+ * transposes, partial sums: ~2 400 floats per sample at D = 75).  The dense layer (4D -> D) runs as three tcgen05 GEMMs at
+ * fp32-equivalent precision, the convolutions one warp per sample (csrc/mke_cnn.cu).  Phase 2: mke_rows_apply_adagrad for
+ * the tables, mke_dense_apply_adagrad for theta (acc0 = 0.1).
  * ------------------------------------------------------------------------------------------ */
 int64_t mke_attr_cnn_param_count(int32_t dim);
 int64_t mke_attr_cnn_workspace_floats(int32_t n, int32_t dim);
