@@ -16,7 +16,14 @@ Pinning status (see DESIGN.md "Oracle"):
     that order to numpy's unstable sorts).
   * device sampler (``oracle/device_sampler.py``): bit-exact restatement of the kernels' counter-based
     sampler; its SEMANTICS (one coin per round, no replacement, filter, exactly K) are checked
-    against the pinned reference restatement statistically and case by case.
+    against the pinned reference restatement statistically and case by case.  Likewise ``sample_distinct``:
+    bit-exact restatement of mke_sample_distinct (the random.sample batches of MultiKE_model.py:355-358, :377, :399,
+    :443, :462 as a keyed permutation); the reference's CPython stream is not reproduced, its semantics (distinct,
+    uniform indices) are what tests/test_device_sampler_oracle.py and tests/test_gpu_refapi.py check.
+  * reference modules and datasets (``oracle/_ref/``, git-ignored, built by __graft_entry__.build() where
+    /root/reference exists): the reference's own code byte-compiled for the unchanged launch scripts
+    (oracle/build_ref.py) and the DBP-YG-100K digests of its own loader / DataModel / PredicateAlignModel
+    (tools/digest_dbp_wd*.py with MKE_DATASET=DBP_YG) for BASELINE configs[3].
   * TF-1.x arithmetic (losses.py, l2_normalize, Adagrad, conv(), the auto-encoder;
     ``oracle/attr_cnn.py``, ``oracle/autoencoder.py``, ``oracle/tf_semantics.py``,
     ``oracle/relation_view.py``): PARITY UNPINNED -- TensorFlow 1.x is a third-party dependency
