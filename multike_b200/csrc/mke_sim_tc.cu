@@ -610,7 +610,11 @@ static void topk_fused_layout(int n, int ws, int k, size_t pitch, size_t& fixed,
 }
 
 bool sim_topk_fused_applies(int n, int k) {
-  return n >= 4 * kTcSample && (long long)k * 8 <= n && n <= 262144 && k >= 64;
+  if (!(n >= 4 * kTcSample && (long long)k * 8 <= n && n <= 262144 && k >= 64)) return false;
+  // the select kernel keeps a row's candidates (2 x cap words) and two bitmaps over the columns in shared memory
+  const long long cap = ((long long)(2.2 * k) + 63) & ~63ll;
+  const long long words = (n + 31) >> 5;
+  return (2 * cap + 2 * words) * 4 <= 200 * 1024;
 }
 
 // hi / lo: prepared rows [n, ws]; work: workspace after them (work_floats floats).  Returns 1 when the workspace is too
