@@ -232,6 +232,8 @@ class MultiKE:
             bounds.append((pos, pos + (e1 - s1) + (e2 - s2)))
             pos += (e1 - s1) + (e2 - s2)
             order += [(0, s1, e1), (1, s2, e2)]
+        if not order:   # no attribute triples (or zero steps): nothing to train
+            order = [(0, 0, 0)]
         epoch_cols = tuple(torch.cat([(c1, c2)[which][k][s:e] for which, s, e in order]) for k in range(4))
         acc = T.new_loss_accumulator(self.device)
         trained = 0
